@@ -1,0 +1,770 @@
+// bayadera_b200 — C-ABI implementation (include/bayadera_b200.h).
+//
+// Host sequencing of the stretch-move sampler and its summary engines; the
+// B200-native replacement of GTXStretch / GTXStretchFactory / GTXDatasetEngine /
+// GTXAcorEngine in
+//   G/ = /root/reference/src/clojure/uncomplicate/bayadera/internal/device/nvidia_gtx.clj
+// Model sources are compiled at run time by NVRTC for sm_100a together with
+// stretch_program.inc; everything model-independent lives in kernels.cuh.
+//
+// libcuda / libnvrtc / libnccl are resolved lazily (dlopen) so that the
+// library loads — and reports BAY_ECUDA loudly — on a machine without a GPU.
+#include "../../include/bayadera_b200.h"
+#include "kernels.cuh"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+#include <nvrtc.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+static const char* kStretchProgram =
+#include "stretch_program.inc"
+    ;
+
+// jitify-style stub so that `#include <stdint.h>` inside model sources resolves under NVRTC
+// (the reference ships the same kind of stub, G/:647).
+static const char* kStdintStub =
+    "#pragma once\n"
+    "typedef signed char int8_t; typedef unsigned char uint8_t;\n"
+    "typedef short int16_t; typedef unsigned short uint16_t;\n"
+    "typedef int int32_t; typedef unsigned int uint32_t;\n"
+    "typedef long long int64_t; typedef unsigned long long uint64_t;\n"
+    "typedef unsigned long long uintptr_t; typedef unsigned long size_t;\n";
+
+// ------------------------------------------------------------------ errors --
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[4096];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(BAY_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),    \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+#define CKLAUNCH()                                                                            \
+    do {                                                                                      \
+        g_launches++;                                                                         \
+        cudaError_t e_ = cudaGetLastError();                                                  \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(BAY_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_),\
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+#define TRY(call)                    \
+    do {                             \
+        int r_ = (call);             \
+        if (r_ != BAY_OK) return r_; \
+    } while (0)
+
+// ------------------------------------------------------- lazy driver/nvrtc --
+namespace {
+
+struct DriverApi {
+    CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*ModuleUnload)(CUmodule) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                             unsigned, CUstream, void**, void**) = nullptr;
+    CUresult (*LaunchCooperativeKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned,
+                                        unsigned, unsigned, CUstream, void**) = nullptr;
+    CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+    CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    bool ok = false;
+};
+
+struct NvrtcApi {
+    nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*,
+                                 const char* const*) = nullptr;
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+    const char* (*GetErrorString)(nvrtcResult) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+
+DriverApi g_cu;
+NvrtcApi g_rtc;
+NcclApi g_nccl;
+std::mutex g_api_mutex;
+
+template <typename F>
+bool drv(const char* name, F* out) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || !p ||
+        q != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    *out = reinterpret_cast<F>(p);
+    return true;
+}
+
+int load_driver() {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (g_cu.ok) return BAY_OK;
+    bool ok = drv("cuModuleLoadData", &g_cu.ModuleLoadData) && drv("cuModuleUnload", &g_cu.ModuleUnload) &&
+              drv("cuModuleGetFunction", &g_cu.ModuleGetFunction) && drv("cuLaunchKernel", &g_cu.LaunchKernel) &&
+              drv("cuLaunchCooperativeKernel", &g_cu.LaunchCooperativeKernel) &&
+              drv("cuFuncGetAttribute", &g_cu.FuncGetAttribute) &&
+              drv("cuFuncSetAttribute", &g_cu.FuncSetAttribute) &&
+              drv("cuOccupancyMaxActiveBlocksPerMultiprocessor",
+                  &g_cu.OccupancyMaxActiveBlocksPerMultiprocessor) &&
+              drv("cuGetErrorString", &g_cu.GetErrorString);
+    if (!ok) return fail(BAY_ECUDA, "CUDA driver entry points unavailable (no NVIDIA driver / GPU?)");
+    g_cu.ok = true;
+    return BAY_OK;
+}
+
+void* open_first(const char* const* names, std::string* why) {
+    for (int i = 0; names[i]; i++) {
+        void* h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+        if (h) return h;
+        *why += std::string(names[i]) + ": " + dlerror() + "; ";
+    }
+    return nullptr;
+}
+
+int load_nvrtc() {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (g_rtc.ok) return BAY_OK;
+    static const char* names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so", nullptr};
+    g_rtc.why.clear();
+    void* h = open_first(names, &g_rtc.why);
+    if (!h) return fail(BAY_ECOMPILE, "cannot load NVRTC: %s", g_rtc.why.c_str());
+#define RTC(sym)                                                                     \
+    g_rtc.sym = reinterpret_cast<decltype(g_rtc.sym)>(dlsym(h, "nvrtc" #sym));       \
+    if (!g_rtc.sym) return fail(BAY_ECOMPILE, "NVRTC symbol nvrtc" #sym " missing");
+    RTC(CreateProgram) RTC(CompileProgram) RTC(GetProgramLogSize) RTC(GetProgramLog) RTC(GetCUBINSize)
+    RTC(GetCUBIN) RTC(DestroyProgram) RTC(GetErrorString)
+#undef RTC
+    g_rtc.ok = true;
+    return BAY_OK;
+}
+
+int load_nccl() {
+    std::lock_guard<std::mutex> lk(g_api_mutex);
+    if (g_nccl.ok) return BAY_OK;
+    static const char* names[] = {"libnccl.so.2", "/usr/lib/x86_64-linux-gnu/libnccl.so.2", nullptr};
+    g_nccl.why.clear();
+    void* h = open_first(names, &g_nccl.why);
+    if (!h) return fail(BAY_ENCCL, "cannot load NCCL: %s", g_nccl.why.c_str());
+#define NC(sym)                                                                      \
+    g_nccl.sym = reinterpret_cast<decltype(g_nccl.sym)>(dlsym(h, "nccl" #sym));      \
+    if (!g_nccl.sym) return fail(BAY_ENCCL, "NCCL symbol nccl" #sym " missing");
+    NC(GetUniqueId) NC(CommInitRank) NC(CommDestroy) NC(AllGather) NC(AllReduce) NC(GroupStart) NC(GroupEnd)
+    NC(GetErrorString)
+#undef NC
+    g_nccl.ok = true;
+    return BAY_OK;
+}
+
+int cu_fail(CUresult r, const char* what) {
+    const char* s = nullptr;
+    if (g_cu.GetErrorString) g_cu.GetErrorString(r, &s);
+    return fail(BAY_ECUDA, "%s failed: %s", what, s ? s : "unknown CUDA driver error");
+}
+
+#define CKNCCL(call)                                                                           \
+    do {                                                                                       \
+        ncclResult_t r_ = (call);                                                              \
+        if (r_ != ncclSuccess) return fail(BAY_ENCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+}  // namespace
+
+// ----------------------------------------------------------------- handles --
+struct bay_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int wgs = 256;
+    int sm_count = 0;
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+struct bay_model {
+    bay_engine* e = nullptr;
+    CUmodule mod = nullptr;
+    CUfunction f_bare = nullptr, f_accu = nullptr, f_logfn = nullptr;
+    int dim = 1, params_size = 0;
+    uint32_t flags = 0;
+    int block = 128;  // bare/logfn block size
+};
+
+struct bay_sampler {
+    bay_model* m = nullptr;
+    int64_t W = 0, H = 0;
+    int D = 1;
+    uint32_t G = 0;  // accu blocks per half
+    float* params = nullptr;
+    bool own_params = false;
+    uint32_t data_len = 0, params_len = 0;
+    float* xs = nullptr;  // D x W SoA, pitch W
+    float* lp = nullptr;  // W
+    uint32_t* accept = nullptr;               // G
+    float* blk_sums = nullptr;                // D x G
+    unsigned long long* accept_total = nullptr;  // 1
+    float* means = nullptr;                   // D x means_cap
+    int64_t means_cap = 0, means_n = 0;
+    uint32_t* hist_counts = nullptr;          // wgs x D
+    uint32_t* mm = nullptr;                   // 2 x D ordered-uint min/max
+    float* limits = nullptr;                  // 2 x D
+    float* pdf = nullptr;                     // wgs x D
+    float* ranks = nullptr;                   // wgs x D
+    double* macc = nullptr;                   // D x 2
+    float* vec_d = nullptr;                   // 4 x D scratch
+    // host-side counters: G/:282-287, 340-400
+    int32_t bare_seed = 0, move_seed = 0;
+    uint32_t bare_counter = 0, move_counter = 0;
+    int64_t iterations = 0;
+    float a_bare = 2.0f, a_move = 2.0f, beta = 1.0f;
+};
+
+// ---------------------------------------------------------------- plumbing --
+static int use_device(const bay_engine* e) {
+    CK(cudaSetDevice(e->device));
+    return BAY_OK;
+}
+
+extern "C" const char* bay_last_error(void) { return g_err.c_str(); }
+extern "C" const char* bay_version(void) { return "bayadera_b200 0.1 (sm_100a)"; }
+extern "C" int64_t bay_launch_count(void) { return g_launches.load(); }
+
+extern "C" int bay_engine_create(int device, uint64_t stream, int wgs, bay_engine** out) {
+    if (!out) return fail(BAY_EINVAL, "out is NULL");
+    if (wgs < 32 || wgs > 1024 || (wgs & (wgs - 1))) return fail(BAY_EINVAL, "wgs must be a power of two in [32, 1024], got %d", wgs);
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(BAY_ECUDA, "no CUDA device available (%s); bayadera_b200 has no CPU fallback",
+                    ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0");
+    }
+    if (device < 0 || device >= count) return fail(BAY_EINVAL, "device %d out of range [0,%d)", device, count);
+    CK(cudaSetDevice(device));
+    CK(cudaFree(0));
+    TRY(load_driver());
+    bay_engine* e = new bay_engine();
+    e->device = device;
+    e->wgs = wgs;
+    CK(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device));
+    if (stream) {
+        e->stream = reinterpret_cast<cudaStream_t>(stream);
+    } else {
+        CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        e->own_stream = true;
+    }
+    *out = e;
+    return BAY_OK;
+}
+
+extern "C" int bay_engine_release(bay_engine* e) {
+    if (!e) return BAY_OK;
+    cudaSetDevice(e->device);
+    if (e->comm && g_nccl.ok) g_nccl.CommDestroy(e->comm);
+    if (e->own_stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return BAY_OK;
+}
+
+extern "C" int bay_engine_processing_elements(bay_engine* e, int64_t* out) {
+    if (!e || !out) return fail(BAY_EINVAL, "NULL argument");
+    *out = (int64_t)e->sm_count * e->wgs;
+    return BAY_OK;
+}
+
+extern "C" int bay_engine_stream(bay_engine* e, uint64_t* s) {
+    if (!e || !s) return fail(BAY_EINVAL, "NULL argument");
+    *s = reinterpret_cast<uint64_t>(e->stream);
+    return BAY_OK;
+}
+
+extern "C" int bay_engine_synchronize(bay_engine* e) {
+    if (!e) return fail(BAY_EINVAL, "NULL engine");
+    TRY(use_device(e));
+    CK(cudaStreamSynchronize(e->stream));
+    return BAY_OK;
+}
+
+extern "C" int bay_nccl_unique_id(uint8_t id_out[128]) {
+    TRY(load_nccl());
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    CKNCCL(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, &id, 128);
+    return BAY_OK;
+}
+
+extern "C" int bay_engine_comm_init(bay_engine* e, const uint8_t id[128], int nranks, int rank) {
+    if (!e || !id) return fail(BAY_EINVAL, "NULL argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(BAY_EINVAL, "bad rank %d / nranks %d", rank, nranks);
+    TRY(load_nccl());
+    TRY(use_device(e));
+    ncclUniqueId uid;
+    memcpy(&uid, id, 128);
+    CKNCCL(g_nccl.CommInitRank(&e->comm, nranks, uid, rank));
+    e->nranks = nranks;
+    e->rank = rank;
+    return BAY_OK;
+}
+
+// ------------------------------------------------------------------- model --
+// NVRTC step shared by bay_model_compile and bay_model_compile_check.
+// gtx-stretch-factory (G/:747-757): model sources first, engine kernels after;
+// stretch-options (G/:630-633) retargeted to sm_100a.
+static int nvrtc_build(const char* const* srcs, int nsrc, const char* logfn_name, int dim, int wgs, int block,
+                       uint32_t flags, bool verbose, std::vector<char>* cubin, std::string* log_out) {
+    if (!srcs || !logfn_name) return fail(BAY_EINVAL, "NULL argument");
+    if (dim < 1 || dim > 4096) return fail(BAY_EINVAL, "dimension %d out of range", dim);
+    if (wgs < 32 || wgs > 1024 || (wgs & (wgs - 1))) return fail(BAY_EINVAL, "wgs must be a power of two in [32, 1024], got %d", wgs);
+    TRY(load_nvrtc());
+    std::string src = "#include <stdint.h>\n";
+    for (int i = 0; i < nsrc; i++) {
+        if (!srcs[i]) return fail(BAY_EINVAL, "srcs[%d] is NULL", i);
+        src += srcs[i];
+        src += "\n";
+    }
+    src += kStretchProgram;
+    std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-default-device", "-lineinfo", "--std=c++17",
+                                     "-DREAL=float", "-DREAL2=float2", "-DACCUMULATOR=float",
+                                     "-DLOGFN=" + std::string(logfn_name), "-DDIM=" + std::to_string(dim),
+                                     "-DWGS=" + std::to_string(wgs), "-DBAY_BLOCK=" + std::to_string(block)};
+    if (flags & BAY_MODEL_FAST_MATH) opts.push_back("-use_fast_math");
+    if (verbose) opts.push_back("--ptxas-options=-v");
+    std::vector<const char*> copts;
+    for (auto& o : opts) copts.push_back(o.c_str());
+
+    nvrtcProgram prog;
+    const char* hdr_src[] = {kStdintStub};
+    const char* hdr_name[] = {"stdint.h"};
+    nvrtcResult r = g_rtc.CreateProgram(&prog, src.c_str(), "bayadera_stretch.cu", 1, hdr_src, hdr_name);
+    if (r != NVRTC_SUCCESS) return fail(BAY_ECOMPILE, "nvrtcCreateProgram: %s", g_rtc.GetErrorString(r));
+    r = g_rtc.CompileProgram(prog, (int)copts.size(), copts.data());
+    size_t n = 0;
+    g_rtc.GetProgramLogSize(prog, &n);
+    std::string log(n + 1, '\0');
+    if (n) g_rtc.GetProgramLog(prog, &log[0]);
+    if (log_out) *log_out = log.c_str();
+    if (r != NVRTC_SUCCESS) {
+        g_rtc.DestroyProgram(&prog);
+        return fail(BAY_ECOMPILE, "NVRTC compilation of model '%s' failed: %s\n%s", logfn_name,
+                    g_rtc.GetErrorString(r), log.c_str());
+    }
+    size_t cs = 0;
+    g_rtc.GetCUBINSize(prog, &cs);
+    cubin->resize(cs);
+    g_rtc.GetCUBIN(prog, cubin->data());
+    g_rtc.DestroyProgram(&prog);
+    return BAY_OK;
+}
+
+static int bare_block_for(int dim) { return dim <= 8 ? 256 : 128; }
+
+extern "C" int bay_model_compile_check(const char* const* srcs, int nsrc, const char* logfn_name, int dim, int wgs,
+                                       uint32_t flags, int64_t* cubin_bytes, char* log_buf, int64_t log_cap) {
+    std::vector<char> cubin;
+    std::string log;
+    int r = nvrtc_build(srcs, nsrc, logfn_name, dim, wgs, bare_block_for(dim), flags, true, &cubin, &log);
+    if (log_buf && log_cap > 0) {
+        const std::string& text = r == BAY_OK ? log : g_err;
+        snprintf(log_buf, (size_t)log_cap, "%s", text.c_str());
+    }
+    if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+    return r;
+}
+
+extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsrc, const char* logfn_name,
+                                 int dim, int params_size, uint32_t flags, bay_model** out) {
+    if (!e || !out) return fail(BAY_EINVAL, "NULL argument");
+    TRY(use_device(e));
+    TRY(load_driver());
+    std::vector<char> cubin;
+    TRY(nvrtc_build(srcs, nsrc, logfn_name, dim, e->wgs, bare_block_for(dim), flags, false, &cubin, nullptr));
+
+    bay_model* m = new bay_model();
+    m->e = e;
+    m->dim = dim;
+    m->params_size = params_size;
+    m->flags = flags;
+    m->block = bare_block_for(dim);
+
+    CUresult cr = g_cu.ModuleLoadData(&m->mod, cubin.data());
+    if (cr != CUDA_SUCCESS) {
+        delete m;
+        return cu_fail(cr, "cuModuleLoadData");
+    }
+    struct { const char* name; CUfunction* f; } fns[] = {
+        {"bay_stretch_bare", &m->f_bare}, {"bay_stretch_accu", &m->f_accu}, {"bay_logfn", &m->f_logfn}};
+    for (auto& fn : fns) {
+        cr = g_cu.ModuleGetFunction(fn.f, m->mod, fn.name);
+        if (cr != CUDA_SUCCESS) {
+            g_cu.ModuleUnload(m->mod);
+            delete m;
+            return cu_fail(cr, fn.name);
+        }
+    }
+    *out = m;
+    return BAY_OK;
+}
+
+extern "C" int bay_model_release(bay_model* m) {
+    if (!m) return BAY_OK;
+    cudaSetDevice(m->e->device);
+    if (m->mod && g_cu.ok) g_cu.ModuleUnload(m->mod);
+    delete m;
+    return BAY_OK;
+}
+
+extern "C" int bay_model_kernel_info(bay_model* m, const char* kernel, int* regs, int* local_bytes, int* smem_bytes) {
+    if (!m || !kernel) return fail(BAY_EINVAL, "NULL argument");
+    CUfunction f = nullptr;
+    CUresult cr = g_cu.ModuleGetFunction(&f, m->mod, kernel);
+    if (cr != CUDA_SUCCESS) return cu_fail(cr, kernel);
+    if (regs) g_cu.FuncGetAttribute(regs, CU_FUNC_ATTRIBUTE_NUM_REGS, f);
+    if (local_bytes) g_cu.FuncGetAttribute(local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, f);
+    if (smem_bytes) g_cu.FuncGetAttribute(smem_bytes, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, f);
+    return BAY_OK;
+}
+
+// ----------------------------------------------------------------- sampler --
+static int launch(bay_engine* e, CUfunction f, unsigned grid, unsigned block, void** args) {
+    CUresult cr = g_cu.LaunchKernel(f, grid, 1, 1, block, 1, 1, 0, reinterpret_cast<CUstream>(e->stream), args, nullptr);
+    if (cr != CUDA_SUCCESS) return cu_fail(cr, "cuLaunchKernel");
+    g_launches++;
+    return BAY_OK;
+}
+
+static void stretch_coeffs(float a, float* cA, float* cB, float* cC) {
+    // z = A u^2 + B u + C (K/engines/nvidia-gtx-mcmc-stretch.cu:69-71), IEEE fp32, source order
+    volatile float inv = 1.0f / a;
+    volatile float t = a - 2.0f;
+    *cA = t + inv;
+    volatile float o = 1.0f - inv;
+    *cB = 2.0f * o;
+    *cC = inv;
+}
+
+static int sampler_alloc(bay_sampler* s) {
+    const bay_engine* e = s->m->e;
+    const size_t W = (size_t)s->W, D = (size_t)s->D, wgs = (size_t)e->wgs;
+    CK(cudaMalloc(&s->xs, sizeof(float) * D * W));
+    CK(cudaMalloc(&s->lp, sizeof(float) * W));
+    CK(cudaMalloc(&s->accept, sizeof(uint32_t) * s->G));
+    CK(cudaMalloc(&s->blk_sums, sizeof(float) * D * s->G));
+    CK(cudaMalloc(&s->accept_total, sizeof(unsigned long long)));
+    CK(cudaMalloc(&s->hist_counts, sizeof(uint32_t) * wgs * D));
+    CK(cudaMalloc(&s->mm, sizeof(uint32_t) * 2 * D));
+    CK(cudaMalloc(&s->limits, sizeof(float) * 2 * D));
+    CK(cudaMalloc(&s->pdf, sizeof(float) * wgs * D));
+    CK(cudaMalloc(&s->ranks, sizeof(float) * wgs * D));
+    CK(cudaMalloc(&s->macc, sizeof(double) * 2 * D));
+    CK(cudaMalloc(&s->vec_d, sizeof(float) * 4 * D));
+    CK(cudaMemsetAsync(s->xs, 0, sizeof(float) * D * W, e->stream));
+    CK(cudaMemsetAsync(s->lp, 0, sizeof(float) * W, e->stream));
+    CK(cudaMemsetAsync(s->accept, 0, sizeof(uint32_t) * s->G, e->stream));
+    CK(cudaMemsetAsync(s->blk_sums, 0, sizeof(float) * D * s->G, e->stream));
+    CK(cudaMemsetAsync(s->hist_counts, 0, sizeof(uint32_t) * wgs * D, e->stream));
+    return BAY_OK;
+}
+
+static int sampler_create_common(bay_model* m, int32_t seed, int64_t walkers, int64_t params_count,
+                                 bay_sampler** out) {
+    if (!m || !out) return fail(BAY_EINVAL, "NULL argument");
+    const int wgs = m->e->wgs;
+    // G/:552, 609-610
+    if (walkers < 2 * wgs || walkers % (2 * wgs) != 0 || walkers > (int64_t)1 << 31)
+        return fail(BAY_EINVAL_WALKERS, "Number of walkers (%lld) must be a multiple of %d.", (long long)walkers, 2 * wgs);
+    if (params_count < 0) return fail(BAY_EINVAL, "negative params_count");
+    TRY(use_device(m->e));
+    bay_sampler* s = new bay_sampler();
+    s->m = m;
+    s->W = walkers;
+    s->H = walkers / 2;
+    s->D = m->dim;
+    s->G = cdiv(s->H, wgs);
+    s->params_len = (uint32_t)m->params_size;
+    // G/:559-560: data-len = max(0, entries(params) - params-size)
+    s->data_len = (uint32_t)(params_count > m->params_size ? params_count - m->params_size : 0);
+    int r = sampler_alloc(s);
+    if (r != BAY_OK) { bay_sampler_release(s); return r; }
+    bay_init(s, seed);
+    *out = s;
+    return BAY_OK;
+}
+
+extern "C" int bay_sampler_create(bay_model* m, int32_t seed, int64_t walkers, const float* params_host,
+                                  int64_t params_count, bay_sampler** out) {
+    if (params_count > 0 && !params_host) return fail(BAY_EINVAL, "params_host is NULL");
+    bay_sampler* s = nullptr;
+    TRY(sampler_create_common(m, seed, walkers, params_count, &s));
+    const size_t bytes = sizeof(float) * (size_t)(params_count > 0 ? params_count : 1);
+    cudaError_t ce = cudaMalloc(&s->params, bytes);
+    if (ce == cudaSuccess && params_count > 0)
+        ce = cudaMemcpyAsync(s->params, params_host, sizeof(float) * params_count, cudaMemcpyHostToDevice, m->e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(m->e->stream);
+    if (ce != cudaSuccess) {
+        bay_sampler_release(s);
+        return fail(BAY_ECUDA, "params upload failed: %s", cudaGetErrorString(ce));
+    }
+    s->own_params = true;
+    *out = s;
+    return BAY_OK;
+}
+
+extern "C" int bay_sampler_create_dev(bay_model* m, int32_t seed, int64_t walkers, uint64_t params_dev,
+                                      int64_t params_count, bay_sampler** out) {
+    bay_sampler* s = nullptr;
+    TRY(sampler_create_common(m, seed, walkers, params_count, &s));
+    s->params = reinterpret_cast<float*>(params_dev);
+    s->own_params = false;
+    *out = s;
+    return BAY_OK;
+}
+
+extern "C" int bay_sampler_release(bay_sampler* s) {
+    if (!s) return BAY_OK;
+    cudaSetDevice(s->m->e->device);
+    cudaStreamSynchronize(s->m->e->stream);
+    if (s->own_params) cudaFree(s->params);
+    void* bufs[] = {s->xs, s->lp, s->accept, s->blk_sums, s->accept_total, s->means, s->hist_counts, s->mm,
+                    s->limits, s->pdf, s->ranks, s->macc, s->vec_d};
+    for (void* b : bufs) if (b) cudaFree(b);
+    delete s;
+    return BAY_OK;
+}
+
+// init! G/:391-400
+extern "C" int bay_init(bay_sampler* s, int32_t seed) {
+    if (!s) return fail(BAY_EINVAL, "NULL sampler");
+    s->bare_seed = seed;
+    s->a_bare = 2.0f;
+    s->beta = 1.0f;
+    s->bare_counter = 0;
+    s->move_seed = seed;
+    return BAY_OK;
+}
+
+static int launch_logfn_all(bay_sampler* s) {
+    bay_model* m = s->m;
+    uint32_t n = (uint32_t)s->W, pitch = (uint32_t)s->W;
+    void* args[] = {&n, &s->data_len, &s->params_len, &s->params, &s->xs, &pitch, &s->lp};
+    return launch(m->e, m->f_logfn, cdiv(n, m->block), m->block, args);
+}
+
+// init-position! [seed limits] G/:409-418
+extern "C" int bay_init_position_uniform(bay_sampler* s, int32_t seed, const float* limits_host) {
+    if (!s || !limits_host) return fail(BAY_EINVAL, "NULL argument");
+    bay_engine* e = s->m->e;
+    TRY(use_device(e));
+    CK(cudaMemcpyAsync(s->limits, limits_host, sizeof(float) * 2 * s->D, cudaMemcpyHostToDevice, e->stream));
+    const uint32_t n4 = (uint32_t)((uint64_t)s->D * s->W / 4);
+    bay::k_init_walkers<<<cdiv(n4, 256), 256, 0, e->stream>>>(n4, (uint32_t)s->D, (uint32_t)seed, s->limits, s->xs,
+                                                           (uint32_t)s->W);
+    CKLAUNCH();
+    TRY(launch_logfn_all(s));
+    // limits_host may be pageable: the async copy above is staged before return, but be safe
+    CK(cudaStreamSynchronize(e->stream));
+    s->iterations = 0;
+    return BAY_OK;
+}
+
+// init-position! [position] G/:401-408
+extern "C" int bay_init_position_from(bay_sampler* s, const bay_sampler* other) {
+    if (!s || !other) return fail(BAY_EINVAL, "NULL argument");
+    if (s->W != other->W || s->D != other->D) return fail(BAY_EINVAL, "samplers differ in shape");
+    bay_engine* e = s->m->e;
+    TRY(use_device(e));
+    CK(cudaMemcpyAsync(s->xs, other->xs, sizeof(float) * (size_t)s->D * s->W, cudaMemcpyDeviceToDevice, e->stream));
+    TRY(launch_logfn_all(s));
+    s->iterations = 0;
+    return BAY_OK;
+}
+
+static int half_bare(bay_sampler* s, int half, uint32_t seed, uint32_t tag, float cA, float cB, float cC,
+                     float beta, uint32_t step) {
+    bay_model* m = s->m;
+    uint32_t K = (uint32_t)s->H, pitch = (uint32_t)s->W;
+    float* act = s->xs + (half ? s->H : 0);
+    float* cmp = s->xs + (half ? 0 : s->H);
+    float* lp = s->lp + (half ? s->H : 0);
+    void* args[] = {&K, &seed, &tag, &s->data_len, &s->params_len, &s->params, &cmp, &act, &pitch, &lp,
+                    &cA, &cB, &cC, &beta, &step};
+    return launch(m->e, m->f_bare, cdiv(K, m->block), m->block, args);
+}
+
+static int half_accu(bay_sampler* s, int half, uint32_t seed, uint32_t tag, float cA, float cB, float cC,
+                     uint32_t step) {
+    bay_model* m = s->m;
+    uint32_t K = (uint32_t)s->H, pitch = (uint32_t)s->W, accumulate = half ? 1u : 0u;
+    float* act = s->xs + (half ? s->H : 0);
+    float* cmp = s->xs + (half ? 0 : s->H);
+    float* lp = s->lp + (half ? s->H : 0);
+    void* args[] = {&K, &seed, &tag, &s->data_len, &s->params_len, &s->params, &cmp, &act, &pitch, &lp,
+                    &s->accept, &s->blk_sums, &cA, &cB, &cC, &step, &accumulate};
+    return launch(m->e, m->f_accu, s->G, m->e->wgs, args);
+}
+
+// move-bare! G/:358-364: odd = (X=s0, S=s1, seed, tag 3333), even = (X=s1, S=s0, seed+1, tag 4444)
+static int move_bare_n(bay_sampler* s, int64_t n, const float* betas /* nullable: use s->beta */) {
+    float cA, cB, cC;
+    stretch_coeffs(s->a_bare, &cA, &cB, &cC);
+    for (int64_t i = 0; i < n; i++) {
+        const float beta = betas ? betas[i] : s->beta;
+        TRY(half_bare(s, 0, (uint32_t)s->bare_seed, 3333u, cA, cB, cC, beta, s->bare_counter));
+        TRY(half_bare(s, 1, (uint32_t)(s->bare_seed + 1), 4444u, cA, cB, cC, beta, s->bare_counter));
+        s->bare_counter++;
+    }
+    return BAY_OK;
+}
+
+extern "C" int bay_move_bare(bay_sampler* s) {
+    if (!s) return fail(BAY_EINVAL, "NULL sampler");
+    TRY(use_device(s->m->e));
+    return move_bare_n(s, 1, nullptr);
+}
+
+// One launch of stretch_move_bare at the current counter (no counter increment): the
+// raw-launch granularity of the reference's kernel-level test
+// (T/internal/nvidia_gtx_test.clj:217-235).  half 0 = odd launch, 1 = even launch.
+extern "C" int bay_move_bare_half(bay_sampler* s, int half) {
+    if (!s || (half != 0 && half != 1)) return fail(BAY_EINVAL, "bad argument");
+    TRY(use_device(s->m->e));
+    float cA, cB, cC;
+    stretch_coeffs(s->a_bare, &cA, &cB, &cC);
+    return half_bare(s, half, (uint32_t)(s->bare_seed + half), half ? 4444u : 3333u, cA, cB, cC, s->beta,
+                     s->bare_counter);
+}
+
+extern "C" int bay_set_a(bay_sampler* s, float a) {
+    if (!s) return fail(BAY_EINVAL, "NULL sampler");
+    s->a_bare = a;
+    return BAY_OK;
+}
+
+extern "C" int bay_set_temperature(bay_sampler* s, float t) {
+    if (!s) return fail(BAY_EINVAL, "NULL sampler");
+    s->beta = (float)(1.0 / (double)t);  // G/:366: (cast-prim (/ 1.0 t))
+    return BAY_OK;
+}
+
+// burn-in! G/:419-429
+extern "C" int bay_burn_in(bay_sampler* s, int64_t n, float a) {
+    if (!s || n < 0) return fail(BAY_EINVAL, "bad argument");
+    TRY(use_device(s->m->e));
+    s->a_bare = a;
+    s->beta = 1.0f;
+    TRY(move_bare_n(s, n, nullptr));
+    s->iterations += n;
+    return BAY_OK;
+}
+
+// anneal! G/:430-440
+extern "C" int bay_anneal(bay_sampler* s, const float* temperature_host, int64_t n, float a) {
+    if (!s || n < 0 || (n > 0 && !temperature_host)) return fail(BAY_EINVAL, "bad argument");
+    TRY(use_device(s->m->e));
+    s->a_bare = a;
+    std::vector<float> betas((size_t)n);
+    for (int64_t i = 0; i < n; i++) betas[i] = (float)(1.0 / (double)temperature_host[i]);
+    TRY(move_bare_n(s, n, betas.data()));
+    if (n > 0) s->beta = betas[n - 1];
+    s->iterations += n;
+    return BAY_OK;
+}
+
+static int ensure_means(bay_sampler* s, int64_t n) {
+    if (s->means_cap >= n) return BAY_OK;
+    int64_t cap = s->means_cap * 2 > n ? s->means_cap * 2 : n;
+    float* fresh = nullptr;
+    CK(cudaMalloc(&fresh, sizeof(float) * (size_t)s->D * cap));
+    if (s->means && s->means_n > 0)
+        CK(cudaMemcpyAsync(fresh, s->means, sizeof(float) * (size_t)s->D * s->means_n, cudaMemcpyDeviceToDevice,
+                           s->m->e->stream));
+    if (s->means) {
+        CK(cudaStreamSynchronize(s->m->e->stream));
+        CK(cudaFree(s->means));
+    }
+    s->means = fresh;
+    s->means_cap = cap;
+    return BAY_OK;
+}
+
+// init-move! G/:340-350 (accept is zero-filled: SURVEY Appendix B-3)
+extern "C" int bay_init_move(bay_sampler* s, float a) {
+    if (!s) return fail(BAY_EINVAL, "NULL sampler");
+    bay_engine* e = s->m->e;
+    TRY(use_device(e));
+    s->move_seed += 2;
+    s->move_counter = 0;
+    s->a_move = a;
+    s->means_n = 0;
+    CK(cudaMemsetAsync(s->accept, 0, sizeof(uint32_t) * s->G, e->stream));
+    CK(cudaMemsetAsync(s->blk_sums, 0, sizeof(float) * (size_t)s->D * s->G, e->stream));
+    return BAY_OK;
+}
+
+// move! G/:351-357: odd = (X=s0, S=s1, move-seed, 1111), even = (X=s1, S=s0, move-seed+1, 2222)
+extern "C" int bay_move(bay_sampler* s) {
+    if (!s) return fail(BAY_EINVAL, "NULL sampler");
+    bay_engine* e = s->m->e;
+    TRY(use_device(e));
+    float cA, cB, cC;
+    stretch_coeffs(s->a_move, &cA, &cB, &cC);
+    TRY(ensure_means(s, s->means_n + 1));
+    TRY(half_accu(s, 0, (uint32_t)s->move_seed, 1111u, cA, cB, cC, s->move_counter));
+    TRY(half_accu(s, 1, (uint32_t)(s->move_seed + 1), 2222u, cA, cB, cC, s->move_counter));
+    const float factor = 0.5f / ((float)e->wgs * (float)s->G);
+    bay::k_step_means<<<cdiv((uint64_t)s->D * 32, 128), 128, 0, e->stream>>>(
+        (uint32_t)s->D, s->G, s->blk_sums, factor, s->means + (size_t)s->means_n * s->D);
+    CKLAUNCH();
+    s->means_n++;
+    s->move_counter++;
+    return BAY_OK;
+}
+
+#include "engine_estimate.inc"

@@ -1,0 +1,427 @@
+// bayadera_b200 — model-independent CUDA kernels (compiled by nvcc for sm_100a).
+//
+// These replace K/cuda/engines/nvidia-gtx-estimate.cu (histogram, min/max,
+// uint_to_real, bitonic_local, mean/variance), the init_walkers /
+// sum_accept_* / sum_means_vertical kernels of nvidia-gtx-mcmc-stretch.cu and
+// K/cuda/engines/nvidia-gtx-acor.cu of the reference
+// (K/ = /root/reference/src/device/uncomplicate/bayadera/internal/device/cuda/).
+//
+// State layout: structure-of-arrays, element (dim d, sample w) at xs[d*pitch + w].
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bay {
+
+// ------------------------------------------------------------------ Philox --
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ float u01(uint32_t i) {
+    return __fmul_rn(__fadd_rn(0.5f, (float)(i >> 9)), 1.1920928955078125e-7f);
+}
+
+// init_walkers (mcmc-stretch.cu:158-195): flat AoS element e = w*D + d gets
+// uniform #(e%4) of Philox counter e/4, mapped into limits[d]; stored SoA.
+__global__ void k_init_walkers(uint32_t n4, uint32_t dim, uint32_t seed,
+                               const float* __restrict__ limits, float* __restrict__ xs,
+                               uint32_t pitch) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n4) return;
+    uint32_t r[4];
+    philox4x32_10(g, 0xf00dcafeu, 0xdeadbeefu, 0xbeeff00du, seed, 0xdecafaaau, r);
+#pragma unroll
+    for (uint32_t c = 0; c < 4; c++) {
+        const uint32_t e = 4u * g + c;
+        const uint32_t w = e / dim, d = e - w * dim;
+        const float lo = limits[2 * d], hi = limits[2 * d + 1];
+        const float u = u01(r[c]);
+        xs[(size_t)d * pitch + w] = __fmaf_rn(u, hi, __fmul_rn(__fsub_rn(1.0f, u), lo));
+    }
+}
+
+// ------------------------------------------------------------- transposes --
+// SoA (dim x n, pitch) -> AoS column-major dim x n (ld = dim): out[w*dim + d]
+__global__ void k_soa_to_aos(const float* __restrict__ xs, uint32_t pitch, uint32_t dim,
+                             uint64_t n, float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const uint64_t w0 = (uint64_t)blockIdx.x * 32;
+    const uint32_t d0 = blockIdx.y * 32;
+    for (uint32_t r = threadIdx.y; r < 32; r += blockDim.y) {
+        const uint32_t d = d0 + r;
+        const uint64_t w = w0 + threadIdx.x;
+        if (d < dim && w < n) tile[r][threadIdx.x] = xs[(size_t)d * pitch + w];
+    }
+    __syncthreads();
+    for (uint32_t r = threadIdx.y; r < 32; r += blockDim.y) {
+        const uint64_t w = w0 + r;
+        const uint32_t d = d0 + threadIdx.x;
+        if (d < dim && w < n) out[w * dim + d] = tile[threadIdx.x][r];
+    }
+}
+
+// AoS view data[offset + ld*col + row] (row < dim) -> SoA
+__global__ void k_aos_to_soa(const float* __restrict__ in, uint64_t offset, uint64_t ld,
+                             uint32_t dim, uint64_t n, float* __restrict__ xs, uint64_t pitch) {
+    __shared__ float tile[32][33];
+    const uint64_t w0 = (uint64_t)blockIdx.x * 32;
+    const uint32_t d0 = blockIdx.y * 32;
+    for (uint32_t r = threadIdx.y; r < 32; r += blockDim.y) {
+        const uint64_t w = w0 + r;
+        const uint32_t d = d0 + threadIdx.x;
+        if (d < dim && w < n) tile[r][threadIdx.x] = in[offset + ld * w + d];
+    }
+    __syncthreads();
+    for (uint32_t r = threadIdx.y; r < 32; r += blockDim.y) {
+        const uint32_t d = d0 + r;
+        const uint64_t w = w0 + threadIdx.x;
+        if (d < dim && w < n) xs[(size_t)d * pitch + w] = tile[threadIdx.x][r];
+    }
+}
+
+// ---------------------------------------------------------------- min/max --
+// Order-preserving float <-> uint32 map so that integer atomics give float min/max.
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+__global__ void k_minmax_init(uint32_t dim, uint32_t* __restrict__ mm) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < dim) { mm[2 * d] = 0xffffffffu; mm[2 * d + 1] = 0u; }
+}
+
+// min_max_reduce (estimate.cu:100-115) over SoA rows; grid = (blocks, dim).
+// Identities are +/-inf, NaNs are ignored.
+__global__ void k_minmax_soa(const float* __restrict__ xs, uint64_t pitch, uint64_t n,
+                             uint32_t* __restrict__ mm) {
+    const uint32_t d = blockIdx.y;
+    const float* row = xs + (size_t)d * pitch;
+    float lo = INFINITY, hi = -INFINITY;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vec = ((pitch & 3) == 0) && ((((uintptr_t)xs) & 15) == 0);
+    if (vec) {
+        const uint64_t n4 = n >> 2;
+        const float4* row4 = reinterpret_cast<const float4*>(row);
+        for (uint64_t q = i; q < n4; q += stride) {
+            const float4 v = __ldg(row4 + q);
+            lo = fminf(fminf(lo, v.x), fminf(fminf(v.y, v.z), v.w));
+            hi = fmaxf(fmaxf(hi, v.x), fmaxf(fmaxf(v.y, v.z), v.w));
+        }
+        for (uint64_t q = (n4 << 2) + i; q < n; q += stride) { lo = fminf(lo, row[q]); hi = fmaxf(hi, row[q]); }
+    } else {
+        for (uint64_t q = i; q < n; q += stride) { lo = fminf(lo, row[q]); hi = fmaxf(hi, row[q]); }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    __shared__ float slo[32], shi[32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) { slo[warp] = lo; shi[warp] = hi; }
+    __syncthreads();
+    if (warp == 0) {
+        lo = lane < nw ? slo[lane] : INFINITY;
+        hi = lane < nw ? shi[lane] : -INFINITY;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (lane == 0) {
+            atomicMin(&mm[2 * d], f2ord(lo));
+            atomicMax(&mm[2 * d + 1], f2ord(hi));
+        }
+    }
+}
+
+__global__ void k_minmax_decode(uint32_t dim, const uint32_t* __restrict__ mm, float* __restrict__ limits) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * dim) limits[i] = ord2f(mm[i]);
+}
+
+// -------------------------------------------------------------- histogram --
+// histogram (estimate.cu:5-32).  bin = clamp(floor(((x-lo)/(hi-lo))*BINS), 0, BINS-1)
+// in IEEE fp32 — integer counts, bit-exact against the oracle.
+__device__ __forceinline__ uint32_t hist_bin(float x, float lo, float range, float fbins, uint32_t bins) {
+    const float t = __fmul_rn(__fdiv_rn(__fsub_rn(x, lo), range), fbins);
+    uint32_t b;
+    if (!(t > 0.0f)) b = 0;
+    else if (t >= fbins) b = bins - 1;
+    else b = (uint32_t)t;
+    return b;
+}
+
+// grid = (chunks, dim).  Shared memory: NSUB privatised sub-histograms of `bins`
+// counters (one per warp group) to cut same-address atomic serialisation when
+// the ensemble concentrates in a few bins; merged with one global atomic per
+// non-empty bin per block.  counts is bins x dim column-major, accumulated.
+__global__ void k_hist_soa(const float* __restrict__ xs, uint64_t pitch, uint64_t n,
+                           const float* __restrict__ limits, uint32_t bins, uint32_t nsub,
+                           uint32_t* __restrict__ counts) {
+    extern __shared__ uint32_t sh[];
+    const uint32_t d = blockIdx.y;
+    for (uint32_t i = threadIdx.x; i < bins * nsub; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const float lo = limits[2 * d], hi = limits[2 * d + 1];
+    const float range = __fsub_rn(hi, lo), fbins = (float)bins;
+    uint32_t* mine = sh + ((threadIdx.x >> 5) % nsub) * bins;
+    const float* row = xs + (size_t)d * pitch;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vec = ((pitch & 3) == 0) && ((((uintptr_t)xs) & 15) == 0);
+    if (vec) {
+        const uint64_t n4 = n >> 2;
+        const float4* row4 = reinterpret_cast<const float4*>(row);
+        for (uint64_t q = i; q < n4; q += stride) {
+            const float4 v = __ldg(row4 + q);
+            atomicAdd(&mine[hist_bin(v.x, lo, range, fbins, bins)], 1u);
+            atomicAdd(&mine[hist_bin(v.y, lo, range, fbins, bins)], 1u);
+            atomicAdd(&mine[hist_bin(v.z, lo, range, fbins, bins)], 1u);
+            atomicAdd(&mine[hist_bin(v.w, lo, range, fbins, bins)], 1u);
+        }
+        for (uint64_t q = (n4 << 2) + i; q < n; q += stride)
+            atomicAdd(&mine[hist_bin(row[q], lo, range, fbins, bins)], 1u);
+    } else {
+        for (uint64_t q = i; q < n; q += stride)
+            atomicAdd(&mine[hist_bin(row[q], lo, range, fbins, bins)], 1u);
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < bins; b += blockDim.x) {
+        uint32_t c = 0;
+        for (uint32_t s = 0; s < nsub; s++) c += sh[s * bins + b];
+        if (c) atomicAdd(&counts[(size_t)bins * d + b], c);
+    }
+}
+
+// uint_to_real (estimate.cu:34-44): pdf = (alpha / (hi-lo)) * count
+__global__ void k_uint_to_real(uint32_t bins, uint32_t dim, float alpha,
+                               const float* __restrict__ limits,
+                               const uint32_t* __restrict__ counts, float* __restrict__ pdf) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t d = blockIdx.y;
+    if (b < bins && d < dim) {
+        const float w = __fsub_rn(limits[2 * d + 1], limits[2 * d]);
+        pdf[(size_t)bins * d + b] = __fmul_rn(__fdiv_rn(alpha, w), (float)counts[(size_t)bins * d + b]);
+    }
+}
+
+// bitonic_local (estimate.cu:117-147): the same compare-exchange network, one
+// block of `bins` threads per dimension, so that the order inside groups of
+// equal mass matches the reference's too.
+__global__ void k_bin_ranks(uint32_t bins, const float* __restrict__ pdf, float* __restrict__ ranks) {
+    extern __shared__ float2 aux[];
+    const uint32_t lid = threadIdx.x;
+    const uint32_t gid = blockIdx.x * bins + lid;
+    float2 value = make_float2((float)lid, pdf[gid]);
+    aux[lid] = value;
+    __syncthreads();
+    for (uint32_t length = 1; length < bins; length <<= 1) {
+        const bool direction = ((lid & (length << 1)) != 0);
+        for (uint32_t inc = length; inc > 0; inc >>= 1) {
+            const uint32_t j = lid ^ inc;
+            const float2 other = aux[j];
+            const bool smaller = (value.y < other.y) || (other.y == value.y && j < lid);
+            const bool swap = smaller ^ (j < lid) ^ direction;
+            value = swap ? other : value;
+            __syncthreads();
+            aux[lid] = value;
+            __syncthreads();
+        }
+    }
+    ranks[gid] = value.x;
+}
+
+// --------------------------------------------------------- mean / variance --
+// mean_reduce + variance_reduce (estimate.cu:149-187) fused into ONE pass over
+// the data: shifted sums S1 = sum(x-p), S2 = sum((x-p)^2) with pivot p = x[d,0]
+// (the shift removes the cancellation of the naive one-pass formula), fp32
+// inside a thread strip, double across threads/blocks.  acc: dim x 2 doubles.
+__global__ void k_moments_soa(const float* __restrict__ xs, uint64_t pitch, uint64_t n,
+                              double* __restrict__ acc) {
+    const uint32_t d = blockIdx.y;
+    const float* row = xs + (size_t)d * pitch;
+    const float p = __ldg(row);
+    double s1 = 0.0, s2 = 0.0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vec = ((pitch & 3) == 0) && ((((uintptr_t)xs) & 15) == 0);
+    if (vec) {
+        const uint64_t n4 = n >> 2;
+        const float4* row4 = reinterpret_cast<const float4*>(row);
+        uint64_t q = i;
+        while (q < n4) {
+            float f1 = 0.f, f2 = 0.f;
+#pragma unroll 4
+            for (int r = 0; r < 8 && q < n4; r++, q += stride) {
+                const float4 v = __ldg(row4 + q);
+                const float a = v.x - p, b = v.y - p, c = v.z - p, e = v.w - p;
+                f1 += (a + b) + (c + e);
+                f2 += (a * a + b * b) + (c * c + e * e);
+            }
+            s1 += (double)f1; s2 += (double)f2;
+        }
+        for (uint64_t t = (n4 << 2) + i; t < n; t += stride) { const float a = row[t] - p; s1 += a; s2 += (double)a * a; }
+    } else {
+        for (uint64_t t = i; t < n; t += stride) { const float a = row[t] - p; s1 += a; s2 += (double)a * a; }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    __shared__ double a1[32], a2[32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) { a1[warp] = s1; a2[warp] = s2; }
+    __syncthreads();
+    if (warp == 0) {
+        s1 = lane < nw ? a1[lane] : 0.0;
+        s2 = lane < nw ? a2[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) { atomicAdd(&acc[2 * d], s1); atomicAdd(&acc[2 * d + 1], s2); }
+    }
+}
+
+// mode 0: mean, 1: population variance, 2: sd
+__global__ void k_moments_finish(uint32_t dim, uint64_t n, const float* __restrict__ xs, uint64_t pitch,
+                                 const double* __restrict__ acc, int mode, float* __restrict__ out) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= dim) return;
+    const double p = (double)xs[(size_t)d * pitch];
+    const double m1 = acc[2 * d] / (double)n;
+    double var = acc[2 * d + 1] / (double)n - m1 * m1;
+    var = var < 0.0 ? 0.0 : var;
+    out[d] = mode == 0 ? (float)(p + m1) : (mode == 1 ? (float)var : (float)sqrt(var));
+}
+
+// ------------------------------------------------- accu-path finalisation --
+// sum_means_vertical + scal! (mcmc-stretch.cu:250-260, nvidia_gtx.clj:457-460)
+// folded into one launch per step: means[step*dim + i] = factor * sum_b blk[i*G + b].
+// One warp per dimension, fixed lane-strided order + shuffle tree (deterministic).
+__global__ void k_step_means(uint32_t dim, uint32_t G, const float* __restrict__ blk_sums,
+                             float factor, float* __restrict__ means_step) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= dim) return;
+    float s = 0.f;
+    for (uint32_t b = lane; b < G; b += 32) s += blk_sums[(size_t)warp * G + b];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) means_step[warp] = s * factor;
+}
+
+// sum_accept_reduce / sum_accept_reduction (mcmc-stretch.cu:240-248): G uint32 -> 1 uint64
+__global__ void k_accept_total(uint32_t G, const uint32_t* __restrict__ accept,
+                               unsigned long long* __restrict__ total) {
+    unsigned long long s = 0;
+    for (uint32_t b = threadIdx.x; b < G; b += blockDim.x) s += accept[b];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ unsigned long long sm[32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) sm[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (uint32_t w = 0; w < nw; w++) t += sm[w];
+        *total = t;
+    }
+}
+
+// ------------------------------------------------------------------- acor --
+// Goodman's acor as the reference runs it (acor.cu:17-168; host
+// nvidia_gtx.clj:230-278) without dynamic parallelism: one CTA per dimension
+// performs mean subtraction, the (c0, d) pass and the halve-and-retry loop.
+// series: dim x n column-major work copy (modified in place).
+// The lag window follows the reference's shared-memory staging rule: a window
+// element in the same WGS-block as t reads 0 when u+lag >= n, one in the next
+// block is read raw (see oracle/bayadera_oracle.c acor_pass).
+__device__ __forceinline__ double block_sum_d(double v, double* sm) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (uint32_t w = 0; w < nw; w++) t += sm[w];
+    return t;
+}
+
+__global__ void k_acor(uint32_t dim, uint32_t n, uint32_t wgs, uint32_t lag, uint32_t min_lag,
+                       uint32_t win_mult, float* __restrict__ series, float* __restrict__ tau,
+                       float* __restrict__ mean, float* __restrict__ sigma) {
+    __shared__ double sm[32];
+    __shared__ double sm2[32];
+    const uint32_t d = blockIdx.x;
+    if (d >= dim) return;
+    // mean and subtraction (sum_reduce_horizontal + subtract_mean, acor.cu:5-28)
+    double s = 0.0;
+    for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) s += (double)series[(size_t)t * dim + d];
+    s = block_sum_d(s, sm);
+    const float mu = (float)(s / (double)n);
+    for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) series[(size_t)t * dim + d] -= mu;
+    __syncthreads();
+
+    uint32_t lag2 = lag, n2 = n, stride = 1;
+    float c0 = 0.f, dv = 0.f, tau_d = 0.f;
+    bool first = true;
+    while (true) {
+        const uint32_t blk = wgs < n2 ? wgs : n2;
+        const size_t st = (size_t)stride * dim;
+        double pc0 = 0.0, pd = 0.0;
+        for (uint32_t t = threadIdx.x; t + lag2 < n2; t += blockDim.x) {
+            const float xt = series[t * st + d];
+            float xacc = 0.f;
+            const uint32_t tb = t / blk;
+            for (uint32_t q = 1; q <= lag2; q++) {
+                const uint32_t u = t + q;
+                const bool zero = ((u / blk) == tb) && !(u + lag2 < n2);
+                xacc += zero ? 0.f : series[u * st + d];
+            }
+            pc0 += (double)__fmul_rn(xt, xt);
+            pd += (double)__fmul_rn(xt, __fadd_rn(xt, __fmul_rn(2.0f, xacc)));
+        }
+        const float c0v = (float)block_sum_d(pc0, sm);
+        dv = (float)block_sum_d(pd, sm2);
+        if (first) { c0 = c0v; first = false; }
+        tau_d = dv / c0;
+        if (!((min_lag < lag2) && ((float)lag2 < tau_d * (float)win_mult))) break;
+        n2 /= 2;
+        lag2 = (lag * win_mult < n2) ? lag : max(10u, n2 / win_mult);
+        __syncthreads();
+        for (uint32_t g = threadIdx.x; g < n2; g += blockDim.x)
+            series[(size_t)(2 * g) * st + d] += series[(size_t)(2 * g + 1) * st + d];
+        stride *= 2;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float scale = (float)stride * (float)(n2 - lag2);
+        tau[d] = dv * (float)(n - lag) / (scale * c0);
+        sigma[d] = sqrtf(dv / (scale * (float)n));
+        mean[d] = mu;
+    }
+}
+
+}  // namespace bay

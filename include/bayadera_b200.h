@@ -1,0 +1,181 @@
+/*
+ * bayadera_b200.h — C ABI of libbayadera_b200.so, the B200-native (sm_100a)
+ * replacement for the device engines of uncomplicate/bayadera.
+ *
+ * Every entry point states the reference interface it replaces.  Aliases:
+ *   P/  = /root/reference/src/clojure/uncomplicate/bayadera/internal/protocols.clj
+ *   G/  = /root/reference/src/clojure/uncomplicate/bayadera/internal/device/nvidia_gtx.clj
+ *   K/  = /root/reference/src/device/uncomplicate/bayadera/internal/device/cuda/
+ *
+ * Conventions
+ *  - Plain C: opaque handles, pointers and sizes only.  No torch / C++ types.
+ *  - Every function returns BAY_OK (0) or a negative bay_status; the message
+ *    of the last failure on the calling thread is bay_last_error().
+ *  - Matrices crossing the boundary use the reference's layout: column-major
+ *    DIM x n, column = one walker / one sample (ld = DIM), fp32.  `limits`
+ *    is 2 x DIM column-major (lo_d, hi_d).  Internally walker state is SoA.
+ *  - Pointers named *_host are host memory, *_dev are device pointers of the
+ *    engine's device; `void* out` + `out_is_device` accepts either.
+ *  - A handle is single-threaded; different handles may be used concurrently.
+ *    All work is enqueued on the engine's stream; calls that return scalars
+ *    or fill host buffers synchronise that stream, the others return after
+ *    enqueue (like the reference: sync only at read-long / transfer).
+ *  - There is NO CPU fallback: without a CUDA device every compute entry
+ *    point fails with BAY_ECUDA.
+ */
+#ifndef BAYADERA_B200_H
+#define BAYADERA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum bay_status {
+    BAY_OK = 0,
+    BAY_EINVAL = -1,          /* bad argument */
+    BAY_EINVAL_WALKERS = -2,  /* G/:609-610 "Number of walkers (%d) must be a multiple of %d." */
+    BAY_EACOR_TOO_SHORT = -3, /* G/:275-278 "The autocorrelation time is too long relative to the variance. ..." */
+    BAY_ECOMPILE = -4,        /* NVRTC rejected the model source; log in bay_last_error() */
+    BAY_ECUDA = -5,           /* CUDA driver/runtime error, or no device */
+    BAY_ENCCL = -6,           /* NCCL error */
+    BAY_ENOTSUP = -7
+} bay_status;
+
+typedef struct bay_engine bay_engine;   /* replaces GTXBayaderaFactory, G/:761-807 */
+typedef struct bay_model bay_model;     /* replaces GTXStretchFactory + its NVRTC module, G/:543-610, 747-757 */
+typedef struct bay_sampler bay_sampler; /* replaces GTXStretch, G/:282-541 */
+
+/* model flags (extra keys of the model's args map; ignored by the reference) */
+#define BAY_MODEL_FAST_MATH   0x1u  /* compile with -use_fast_math like G/:630-633 (default of the host mirror) */
+#define BAY_MODEL_ROW_ADDITIVE 0x2u /* model also defines BAY_ROWLIK / BAY_PRIOR */
+#define BAY_MODEL_GLM_LOGISTIC 0x4u /* data rows are [y, x_1..x_D]; likelihood is Bernoulli-logit of x·theta */
+
+const char *bay_last_error(void);
+const char *bay_version(void);
+
+/* ---- engine: gtx-bayadera-factory [ctx hstream compute-units WGS], G/:791-807 ----
+ * device: CUDA ordinal.  stream: a CUstream/cudaStream_t handle to enqueue on,
+ * or 0 to let the engine create its own non-blocking stream.  wgs: the
+ * reference's work-group size = histogram bin count = accu block size
+ * (power of two, 32..1024; the reference default is max-block-dim-x = 1024,
+ * its tests use 256). */
+int bay_engine_create(int device, uint64_t stream, int wgs, bay_engine **out);
+int bay_engine_release(bay_engine *e);
+/* processing-elements, P/:138, G/:788-789  (= SM count * WGS) */
+int bay_engine_processing_elements(bay_engine *e, int64_t *out);
+int bay_engine_stream(bay_engine *e, uint64_t *stream_out);
+int bay_engine_synchronize(bay_engine *e);
+
+/* ---- multi-GPU: one process per GPU; no counterpart in the reference ----
+ * The 128-byte ncclUniqueId is produced on rank 0 and distributed by the
+ * caller (torch.distributed broadcast in the host mirror). */
+int bay_nccl_unique_id(uint8_t id_out[128]);
+int bay_engine_comm_init(bay_engine *e, const uint8_t id[128], int nranks, int rank);
+
+/* ---- model: mcmc-factory [this model], P/:137; gtx-stretch-factory G/:747-757 ----
+ * srcs: the model's (source) vector of C strings, concatenated in order;
+ * logfn_name: (mcmc-logpdf model); dim: (dimension model);
+ * params_size: (params-size model).  The source is compiled by NVRTC for
+ * sm_100a together with the engine's stretch kernels. */
+int bay_model_compile(bay_engine *e, const char *const *srcs, int nsrc, const char *logfn_name,
+                      int dim, int params_size, uint32_t flags, bay_model **out);
+int bay_model_release(bay_model *m);
+/* device-less NVRTC build of the same program (the CPU "does it build" gate; log receives the
+ * ptxas -v register/spill report, or the compiler errors). */
+int bay_model_compile_check(const char *const *srcs, int nsrc, const char *logfn_name, int dim, int wgs,
+                            uint32_t flags, int64_t *cubin_bytes, char *log_buf, int64_t log_cap);
+/* registers/spills/shared of the compiled stretch kernel (profiling aid) */
+int bay_model_kernel_info(bay_model *m, const char *kernel, int *regs, int *local_bytes, int *smem_bytes);
+
+/* ---- sampler: create-sampler [this seed walkers params], P/:120-121, G/:548-610 ----
+ * params_host = [data (data_len) || hyperparams (params_size)], copied.
+ * Fails with BAY_EINVAL_WALKERS unless walkers >= 2*wgs and walkers % (2*wgs) == 0.
+ * With a communicator (bay_engine_comm_init) `walkers` is the GLOBAL count. */
+int bay_sampler_create(bay_model *m, int32_t seed, int64_t walkers, const float *params_host,
+                       int64_t params_count, bay_sampler **out);
+/* same, with params already in device memory (the reference borrows a cuda-float vector) */
+int bay_sampler_create_dev(bay_model *m, int32_t seed, int64_t walkers, uint64_t params_dev,
+                           int64_t params_count, bay_sampler **out);
+int bay_sampler_release(bay_sampler *s);
+
+/* MCMC protocol, P/:97-103 */
+int bay_init(bay_sampler *s, int32_t seed);                                          /* init!          G/:391-400 */
+int bay_init_position_uniform(bay_sampler *s, int32_t seed, const float *limits_host); /* init-position! [seed limits] G/:409-418 */
+int bay_init_position_from(bay_sampler *s, const bay_sampler *other);                /* init-position! [position]    G/:401-408 */
+int bay_burn_in(bay_sampler *s, int64_t n, float a);                                 /* burn-in!       G/:419-429 */
+/* anneal!: the Clojure schedule fn i -> T is pre-evaluated by the caller into temperature[n] */
+int bay_anneal(bay_sampler *s, const float *temperature_host, int64_t n, float a);   /* anneal!        G/:430-440 */
+int bay_acc_rate(bay_sampler *s, float a, double *out);                              /* acc-rate!      G/:466-478 */
+/* run-sampler!: returns acceptance rate and Autocorrelation{tau mean sigma steps lag}
+ * (tau/mean/sigma: DIM floats each, host). BAY_EACOR_TOO_SHORT when 5*lag > n. */
+int bay_run_sampler(bay_sampler *s, int64_t n, float a, double *acc_rate, float *tau_host,
+                    float *mean_host, float *sigma_host, int64_t *lag);              /* run-sampler!   G/:441-465 */
+/* per-step ensemble means of the last run-sampler!/acc-rate! (DIM x n, column = step) */
+int bay_last_means(bay_sampler *s, float *means_host, int64_t n);
+
+/* MCMCStretch protocol, P/:105-109 */
+int bay_init_move(bay_sampler *s, float a);          /* init-move!       G/:340-350 */
+int bay_move(bay_sampler *s);                        /* move!            G/:351-357 */
+int bay_move_bare(bay_sampler *s);                   /* move-bare!       G/:358-364 */
+int bay_set_temperature(bay_sampler *s, float t);    /* set-temperature! G/:365-369 */
+/* one raw launch of stretch_move_bare at the current counter, counter NOT advanced: the granularity of the
+ * reference's kernel-level test (T/internal/nvidia_gtx_test.clj:217-235). half 0 = odd (s0), 1 = even (s1). */
+int bay_move_bare_half(bay_sampler *s, int half);
+int bay_set_a(bay_sampler *s, float a);              /* the `a` slot of the bare parameter packs, G/:423-424 */
+/* raw results of the accu path (the reference's cu-accept / cu-means-acc buffers,
+ * pinned at T/internal/nvidia_gtx_test.clj:251-254): per-block accept counts
+ * (G = ceil(H/wgs) uint32) and the per-block position sums of the last move (DIM x G). */
+int bay_accu_blocks(bay_sampler *s, uint32_t *accept_host, float *block_sums_host);
+
+/* RandomSampler protocol, P/:94-95: sample! G/:371-389.  out is DIM x n. */
+int bay_sample(bay_sampler *s, int64_t n, void *out, int out_is_device);
+
+/* EstimateEngine / Location / Spread on the sampler, P/:20-28, 82-84; G/:482-541.
+ * Histogram{limits 2xDIM, pdf WGSxDIM, bin-ranks WGSxDIM}, host fp32. */
+int bay_histogram(bay_sampler *s, int64_t cycles, float *limits_host, float *pdf_host,
+                  float *bin_ranks_host);
+/* raw bin counts of the last bay_histogram (WGS x DIM uint32) — bit-exact parity hook */
+int bay_histogram_counts(bay_sampler *s, uint32_t *counts_host);
+int bay_mean(bay_sampler *s, float *out_host);
+int bay_variance(bay_sampler *s, float *out_host);
+int bay_sd(bay_sampler *s, float *out_host);
+
+/* Info, G/:332-335 */
+int bay_info(bay_sampler *s, int64_t *walkers, int64_t *iterations);
+
+/* state hand-off (SURVEY §5 checkpoint/resume): positions DIM x W (host, AoS),
+ * log-densities W, and the three integers that with the seed determine the
+ * Philox stream: move-seed, move-bare-counter, move-counter. */
+int bay_get_state(bay_sampler *s, float *xs_host, float *logfn_host, int32_t *bare_seed,
+                  int32_t *move_seed, int64_t *bare_counter, int64_t *move_counter);
+int bay_set_state(bay_sampler *s, const float *xs_host, const float *logfn_host /* NULL: recompute */,
+                  int32_t bare_seed, int32_t move_seed, int64_t bare_counter, int64_t move_counter);
+
+/* ---- DatasetEngine / EstimateEngine on an arbitrary matrix, P/:71-73, 82-84; G/:145-228 ----
+ * data: m x n, element (row, col) at data[offset + ld*col + row]. */
+int bay_dataset_mean(bay_engine *e, const void *data, int data_is_device, int64_t m, int64_t n,
+                     int64_t offset, int64_t ld, float *mean_host);
+int bay_dataset_variance(bay_engine *e, const void *data, int data_is_device, int64_t m, int64_t n,
+                         int64_t offset, int64_t ld, float *variance_host);
+int bay_dataset_histogram(bay_engine *e, const void *data, int data_is_device, int64_t m, int64_t n,
+                          int64_t offset, int64_t ld, float *limits_host, float *pdf_host,
+                          float *bin_ranks_host, uint32_t *counts_host /* nullable */);
+
+/* ---- AcorEngine, P/:86-87; G/:230-278.  series: dim x n (column = step), host. ---- */
+int bay_acor(bay_engine *e, const float *series_host, int64_t dim, int64_t n, float *tau_host,
+             float *mean_host, float *sigma_host, int64_t *lag);
+
+/* ---- DensityEngine on the sampler's model: the logfn kernel over a point matrix
+ * (K/engines/nvidia-gtx-mcmc-stretch.cu:197-206).  x: DIM x n. */
+int bay_model_logfn(bay_model *m, const float *params_host, int64_t params_count,
+                    const float *x_host, int64_t n, float *out_host);
+
+/* profiling counters: kernels launched by this library on the calling process */
+int64_t bay_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAYADERA_B200_H */

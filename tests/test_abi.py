@@ -1,0 +1,96 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads, exports every symbol the header declares,
+fails loudly without a GPU, and NVRTC builds every model for sm_100a (no compute calls here)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import bayadera_b200 as bb
+from bayadera_b200 import _lib, models
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def header_symbols():
+    text = (ROOT / "include" / "bayadera_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bay_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol():
+    L = _lib.load()
+    syms = header_symbols()
+    assert len(syms) >= 40
+    for name in syms:
+        assert hasattr(L, name), f"{name} declared in the header but not exported"
+
+
+def test_python_binding_covers_header():
+    assert sorted(_lib.SIGNATURES) == header_symbols()
+
+
+def _cuda():
+    import torch
+    return torch.cuda.is_available()
+
+
+@pytest.mark.skipif(_cuda(), reason="this checks the no-GPU failure mode")
+def test_no_cpu_fallback_without_gpu():
+    with pytest.raises(bb.BayaderaError, match="no CPU fallback|CUDA"):
+        bb.B200BayaderaFactory(device=0, wgs=256)
+
+
+def _compile_check(model, wgs=256):
+    L = _lib.load()
+    srcs = (C.c_char_p * len(model.source))(*[s.encode() for s in model.source])
+    n = C.c_int64()
+    log = C.create_string_buffer(1 << 16)
+    rc = L.bay_model_compile_check(srcs, len(model.source), model.mcmc_logpdf.encode(), model.dimension, wgs,
+                                   model.flags, C.byref(n), log, len(log))
+    return rc, n.value, log.value.decode("utf-8", "replace")
+
+
+ALL_MODELS = list(models.DISTRIBUTIONS.values()) + [
+    models.beta_binomial_posterior(),
+    models.posterior_model(models.GAUSSIAN, "gg", models.GAUSSIAN),
+    models.therapeutic_touch_model(),
+    models.logistic_regression_model(64),
+    models.mvn_model(100),
+]
+
+
+@pytest.mark.parametrize("model", ALL_MODELS, ids=lambda m: m.name)
+def test_nvrtc_builds_model_for_sm100a(model):
+    rc, nbytes, log = _compile_check(model)
+    assert rc == 0, log
+    assert nbytes > 1000
+    assert "sm_100a" in log                      # ptxas -v report names the target
+    for kernel in ("bay_stretch_bare", "bay_stretch_accu", "bay_logfn"):
+        assert kernel in log
+
+
+def test_nvrtc_error_is_reported():
+    bad = models.DeviceModel("bad", ("extern \"C\" { inline REAL bad_logpdf(int x) { return undefined_symbol; } }",),
+                             "bad_logpdf")
+    rc, _, log = _compile_check(bad)
+    assert rc == _lib.ECOMPILE
+    assert "undefined_symbol" in log
+
+
+def test_wgs_validation():
+    rc, _, log = _compile_check(models.GAUSSIAN, wgs=100)
+    assert rc == _lib.EINVAL and "power of two" in log
+
+
+def test_parameter_vectors():
+    p = models.beta_params(3, 2)
+    assert p.dtype == np.float32 and np.isclose(p[2], np.log(12.0), rtol=1e-6)   # -lbeta(3,2) = log 12
+    v, mu, sigma = models.mvn_params(8, seed=1)
+    u = np.zeros((8, 8))
+    at = 8
+    for i in range(8):
+        u[i, i:] = v[at:at + 8 - i]
+        at += 8 - i
+    assert np.allclose(np.linalg.inv(u.T @ u), sigma, rtol=2e-3, atol=1e-3)

@@ -1,0 +1,385 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the CPU oracle and the reference's goldens.
+
+Bar (north_star): Philox / proposal / init / histogram-count arithmetic bit-exact; per-walker logpdf within
+1e-5 relative; accept decisions equal except at near-ties |u - q| <= tie_tol * q (fast-math exp/pow on the GPU vs
+libm on the CPU); chain-level results statistical.
+"""
+import numpy as np
+import pytest
+
+import goldens as G
+import bayadera_b200 as bb
+from bayadera_b200 import mcmc, models
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+LOGPDF_RTOL = 1e-5       # north_star: per-walker logpdf within 1e-5 relative
+TIE_TOL = 2e-4           # near-tie band on the accept ratio (fast-math exp: ~2 ulp * |arg|)
+
+
+def f32(x):
+    return np.asarray(x, dtype=np.float32)
+
+
+@pytest.fixture(scope="module")
+def factory():
+    f = bb.B200BayaderaFactory(device=0, wgs=G.WGS)
+    yield f
+    f.release()
+
+
+def make_pair(factory, model, seed, walkers, params, limits, wgs=G.WGS):
+    sf = factory.mcmc_factory(model)
+    gpu = sf.create_sampler(seed, walkers, params)
+    cpu = orc.OracleStretch(model, seed, walkers, params, wgs=wgs)
+    gpu.init(seed).init_position(seed, limits)
+    cpu.init(seed).init_position(seed, limits)
+    return sf, gpu, cpu
+
+
+def logpdf_close(a, b, rtol=LOGPDF_RTOL):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    both_nan = np.isnan(a) & np.isnan(b)
+    same_inf = np.isinf(a) & (a == b)
+    fin = np.isfinite(a) & np.isfinite(b)
+    ok = both_nan | same_inf | (fin & (np.abs(a - b) <= rtol * np.maximum(np.abs(a), np.abs(b)) + 1e-6))
+    return ok
+
+
+# ------------------------------------------------------------------ reference goldens on the GPU --
+def test_golden_uniform_positions(factory):
+    sf, gpu, _ = make_pair(factory, models.UNIFORM, G.SEED, G.W, f32([-1, 2]), f32([-1, 2]))
+    for want in G.UNIFORM_SAMPLES:
+        got = gpu.sample()[:4, 0]
+        assert np.array_equal(got, f32(want)), (got, want)
+    assert gpu.info() == {"walker-count": G.W, "iteration-counter": 4}
+
+
+def test_golden_raw_launches_and_accu_step(factory):
+    sf, gpu, _ = make_pair(factory, models.UNIFORM, G.SEED, G.W, f32([-1, 2]), f32([-1, 2]))
+    # raw launches with explicit step counters (nvidia_gtx_test.clj:217-235)
+    for step, want in enumerate(G.UNIFORM_SAMPLES[:2]):
+        gpu.set_state(bare_counter=step)
+        gpu.move_bare_half(0).move_bare_half(1)
+        assert np.array_equal(gpu.get_state()["xs"][:4, 0], f32(want))
+    # one accu step with seeds (123, 124), tags 1111/2222, step 0 (nvidia_gtx_test.clj:237-258)
+    gpu.set_state(move_seed=G.SEED - 2)
+    gpu.init_move(G.A).move()
+    assert np.array_equal(gpu.get_state()["xs"][:4, 0], f32(G.UNIFORM_ACCU_XS))
+    accept, sums = gpu.accu_blocks()
+    assert tuple(int(v) for v in accept[:10]) == G.UNIFORM_ACCU_ACCEPT
+    assert np.array_equal(sums[0, :10], f32(G.UNIFORM_ACCU_BLOCK_SUMS))
+    assert abs(float(sums.astype(np.float64).sum()) - G.UNIFORM_ACCU_TOTAL) < 2e-3
+    assert abs(float(gpu.last_means(1)[0, 0]) - G.UNIFORM_ACCU_TOTAL / G.W) < 1e-6
+
+
+def test_golden_gaussian_positions(factory):
+    sf, gpu, _ = make_pair(factory, models.GAUSSIAN, G.SEED, G.W, f32([3, 1.0]), f32([-7, 7]))
+    for want in G.GAUSSIAN_SAMPLES:
+        got = gpu.sample()[:4, 0]
+        assert np.array_equal(got, f32(want)), (got, want)
+
+
+def test_golden_burn_in_summary(factory):
+    sf = factory.mcmc_factory(models.GAUSSIAN)
+    gpu = sf.create_sampler(G.SEED, G.W, f32([3, 1.0]))
+    gpu.init_position(G.SEED, f32([-7, 7]))
+    gpu.init(G.SEED + 1)
+    gpu.burn_in(100, 1.5)
+    ds = factory.dataset_engine()
+    assert abs(float(ds.data_mean(gpu.sample())[0]) - G.BURN_IN_CUDA["mean"]) < 2e-3
+    strided = gpu.sample()[::1500, 0]
+    assert np.allclose(strided, f32(G.BURN_IN_CUDA["strided"]), atol=5e-3)
+    assert abs(float(np.sqrt(ds.data_variance(gpu.sample())[0])) - G.BURN_IN_CUDA["sd"]) < 2e-3
+
+
+def test_acc_rate_and_tau(factory):
+    sf = factory.mcmc_factory(models.GAUSSIAN)
+    gpu = sf.create_sampler(G.SEED, 2 * G.W, f32([200, 1]))
+    gpu.init(G.SEED).init_position(G.SEED, f32([180.0, 220.0]))
+    gpu.burn_in(5120, 8.0)
+    assert abs(gpu.acc_rate(8.0) - G.ACC_RATE_OPENCL) < 1.5e-3
+    res = gpu.run_sampler(63670, 8.0)
+    assert abs(float(res["autocorrelation"].tau[0]) - G.TAU) < 0.5
+    assert abs(float(res["autocorrelation"].mean[0]) - 200.0) < 0.01
+    assert 0.48 < res["acceptance-rate"] < 0.49
+    assert gpu.info()["iteration-counter"] == 5120 + 1 + 63670
+
+
+@pytest.mark.parametrize("n", [67, 367, 112640])
+def test_acor_fixtures(factory, n):
+    series = G.acor_fixture(n)
+    ac = factory.acor_engine().acor(series)
+    tau, mean, sigma, lag = orc.acor(series, 2, n, G.WGS)
+    assert ac.lag == lag and ac.steps == n
+    assert np.allclose(ac.tau, tau, rtol=2e-5) and np.allclose(ac.sigma, sigma, rtol=2e-5)
+    assert np.allclose(ac.mean, mean, rtol=1e-6, atol=1e-7)
+    want = G.ACOR[n]
+    if n == 112640:
+        assert abs(float(ac.tau[1]) - want["tau"]) < 1e-3 and abs(float(ac.sigma[0]) - want["sigma"]) < 1e-3
+    else:
+        assert np.allclose(ac.tau, want["tau"], rtol=2e-5) and abs(float(ac.sigma[0]) - want["sigma"]) < 2e-5
+
+
+def test_acor_too_short(factory):
+    with pytest.raises(bb.AcorTooShortError, match="must not be less than 50"):
+        factory.acor_engine().acor(np.zeros((40, 1), dtype=np.float32))
+
+
+# --------------------------------------------------------------------------- kernel-level parity --
+MODEL_CASES = [
+    ("gaussian", models.GAUSSIAN, f32([3, 1.0]), f32([-7, 7])),
+    ("student_t", models.STUDENT_T, f32([5, 1.0, 2.0, 0.0]), f32([-10, 12])),
+    ("beta", models.BETA, models.beta_params(3, 2), f32([0, 1])),
+    ("gamma", models.GAMMA, f32([2.0, 3.0, 0.0]), f32([0.01, 20])),
+    ("erlang", models.ERLANG, f32([2.0, 3.0, 0.0]), f32([0.01, 10])),
+    ("exponential", models.EXPONENTIAL, f32([4.0, np.log(4.0)]), f32([-0.5, 3])),   # part of the box is out of support
+    ("beta_binomial", models.beta_binomial_posterior(),
+     np.concatenate([models.binomial_lik_params(50, 15), models.beta_params(3, 2)]), f32([0, 1])),
+]
+
+
+@pytest.mark.parametrize("name,model,params,limits", MODEL_CASES, ids=[c[0] for c in MODEL_CASES])
+def test_init_logfn_and_steplocked_moves(factory, name, model, params, limits):
+    W = 4 * G.WGS * 8
+    sf, gpu, cpu = make_pair(factory, model, 77, W, params, limits)
+    st = gpu.get_state()
+    assert np.array_equal(st["xs"].reshape(-1), cpu.xs), "init_walkers must be bit-exact"
+    assert logpdf_close(st["logfn"], cpu.lp).all(), "logfn kernel vs oracle"
+    check_steplocked(gpu, cpu, steps=6, a=2.0)
+
+
+def check_steplocked(gpu, cpu, steps, a, beta_t=1.0, tie_tol=TIE_TOL):
+    """Per half-step: both engines start from the oracle's state; compare accept masks (modulo near-ties),
+    positions of agreeing walkers bit-for-bit and the accepted proposals' log-densities."""
+    D, H = cpu.D, cpu.H
+    cpu.a_bare = a
+    cpu.set_temperature(beta_t)
+    gpu.set_a(a).set_temperature(beta_t)
+    mism_total = 0
+    for step in range(steps):
+        for half in (0, 1):
+            before_x, before_lp = cpu.xs.copy(), cpu.lp.copy()
+            gpu.set_state(xs=before_x, logfn=before_lp, bare_counter=cpu.bare_counter)
+            cpu.half_bare(half, want_diag=True)
+            gpu.move_bare_half(half)
+            g = gpu.get_state()
+            gx, glp = g["xs"].reshape(-1, D), g["logfn"]
+            cx = cpu.xs.reshape(-1, D)
+            sl = slice(half * H, (half + 1) * H)
+            other = slice((1 - half) * H, (2 - half) * H)
+            assert np.array_equal(gx[other], cx[other]), "complementary half must be untouched"
+            acc_cpu = cpu.diag["acc"].astype(bool)
+            moved_gpu = ~np.all(gx[sl] == before_x.reshape(-1, D)[sl], axis=1) | (glp[sl] != before_lp[sl])
+            # a GPU accept with Y == X bit-for-bit cannot be seen from outside; irrelevant for parity
+            q, uz = cpu.diag["q"].astype(np.float64), cpu.diag["uz"].astype(np.float64)
+            near_tie = np.abs(uz - q) <= tie_tol * np.maximum(q, 1e-30)
+            same_pos = np.all(gx[sl] == cx[sl], axis=1)
+            bad = ~same_pos & ~near_tie
+            assert not bad.any(), (f"step {step} half {half}: {bad.sum()} walkers differ outside the near-tie band; "
+                                   f"first k={np.flatnonzero(bad)[:5]}, q={q[bad][:5]}, uz={uz[bad][:5]}")
+            mism_total += int((~same_pos).sum())
+            agree_acc = same_pos & acc_cpu
+            assert logpdf_close(glp[sl][agree_acc], cpu.lp[sl][agree_acc]).all(), "accepted log-density parity"
+            assert np.array_equal(glp[sl][same_pos & ~acc_cpu], before_lp[sl][same_pos & ~acc_cpu])
+            del moved_gpu
+        cpu.bare_counter += 1
+    assert mism_total <= max(2, int(2e-4 * steps * 2 * H)), f"too many near-tie mismatches: {mism_total}"
+
+
+def test_steplocked_annealed_and_large_a(factory):
+    model, params = models.GAUSSIAN, f32([200, 1])
+    sf, gpu, cpu = make_pair(factory, model, 5, 2048, params, f32([180, 220]))
+    check_steplocked(gpu, cpu, steps=4, a=8.0, beta_t=7.0)
+    check_steplocked(gpu, cpu, steps=4, a=1.5, beta_t=1.0)
+
+
+def test_therapeutic_touch_d30(factory):
+    model = models.therapeutic_touch_model()
+    params = models.therapeutic_touch_data()
+    sf, gpu, cpu = make_pair(factory, model, 11, 4096, params, model.limits_array())
+    st = gpu.get_state()
+    assert np.array_equal(st["xs"].reshape(-1), cpu.xs)
+    assert logpdf_close(st["logfn"], cpu.lp, rtol=2e-5).all()
+    check_steplocked(gpu, cpu, steps=4, a=2.0, tie_tol=2e-3)   # z^(D-1) with D = 30 widens the fast-math band
+
+
+def test_mvn_d100(factory):
+    model = models.mvn_model(100)
+    params, _, _ = models.mvn_params(100)
+    sf, gpu, cpu = make_pair(factory, model, 3, 2048, params, model.limits_array())
+    st = gpu.get_state()
+    assert np.array_equal(st["xs"].reshape(-1), cpu.xs)
+    assert logpdf_close(st["logfn"], cpu.lp, rtol=5e-5).all()    # 5050-term fp32 sums, fma vs mul+add
+    check_steplocked(gpu, cpu, steps=2, a=1.2, tie_tol=5e-2)
+
+
+def test_logistic_regression_small(factory):
+    d, rows = 8, 500
+    rng = np.random.default_rng(2024)
+    x = rng.standard_normal((rows, d)).astype(np.float32)
+    theta = (rng.standard_normal(d) / np.sqrt(8)).astype(np.float32)
+    y = (rng.random(rows) < 1 / (1 + np.exp(-(x @ theta)))).astype(np.float32)
+    data = np.concatenate([y[:, None], x], axis=1).reshape(-1)
+    model = models.logistic_regression_model(d)
+    params = np.concatenate([data, f32([1.0 / (2 * 10.0 ** 2)])])
+    sf, gpu, cpu = make_pair(factory, model, 9, 1024, params, model.limits_array())
+    st = gpu.get_state()
+    assert logpdf_close(st["logfn"], cpu.lp, rtol=2e-5).all()
+    check_steplocked(gpu, cpu, steps=3, a=2.0, tie_tol=5e-3)
+
+
+def test_uniform_chain_bit_exact_over_many_steps(factory):
+    """The uniform model's accept test is exact (q is 0 or 1), so whole chains must agree bit-for-bit."""
+    sf, gpu, cpu = make_pair(factory, models.UNIFORM, G.SEED, G.W, f32([-1, 2]), f32([-1, 2]))
+    gpu.burn_in(200, 2.0)
+    cpu.burn_in(200, 2.0)
+    gpu.anneal(mcmc.minus_n(50.0), 50, 3.0)
+    cpu.anneal(mcmc.minus_n(50.0), 50, 3.0)
+    assert np.array_equal(gpu.get_state()["xs"].reshape(-1), cpu.xs)
+    a, b = gpu.sample(3 * G.W + 100), cpu.sample(3 * G.W + 100)
+    assert np.array_equal(a, b)
+    assert gpu.info()["iteration-counter"] == cpu.iterations == 254
+
+
+def test_run_sampler_means_and_accept_parity_uniform(factory):
+    sf, gpu, cpu = make_pair(factory, models.UNIFORM, G.SEED, G.W, f32([-1, 2]), f32([-1, 2]))
+    rg = gpu.run_sampler(64, 2.0)
+    rc = cpu.run_sampler(64, 2.0)
+    assert rg["acceptance-rate"] == rc["acceptance-rate"]            # integer counts: exact
+    acc_g, sums_g = gpu.accu_blocks()
+    assert np.array_equal(acc_g, cpu.accept)
+    assert np.array_equal(sums_g.reshape(-1), cpu.blk_sums)          # block tree order: exact
+    assert np.allclose(gpu.last_means(64), rc["means"], rtol=1e-6, atol=1e-7)
+    ag, ac = rg["autocorrelation"], rc["autocorrelation"]
+    assert ag.lag == ac["lag"] and np.allclose(ag.tau, ac["tau"], rtol=1e-3)
+
+
+# --------------------------------------------------------------------------------- estimate engine --
+def test_histogram_counts_bit_exact_with_cycles(factory):
+    sf, gpu, cpu = make_pair(factory, models.UNIFORM, G.SEED, G.W, f32([-1, 2]), f32([-1, 2]))
+    gpu.burn_in(20, 2.0)
+    cpu.burn_in(20, 2.0)
+    hg = gpu.histogram(5)
+    hc = cpu.histogram(5)
+    assert np.array_equal(hg.limits, hc["limits"])
+    assert np.array_equal(gpu.histogram_counts(), hc["counts"])
+    assert int(gpu.histogram_counts().sum()) == 5 * G.W
+    assert np.array_equal(hg.pdf, hc["pdf"])
+    assert np.array_equal(hg.bin_ranks, hc["bin-ranks"])
+    assert gpu.info()["iteration-counter"] == 24
+
+
+def test_histogram_and_moments_multidim(factory):
+    model = models.mvn_model(100)
+    params, mu, sigma = models.mvn_params(100)
+    sf, gpu, cpu = make_pair(factory, model, 3, 8192, params, model.limits_array())
+    st = gpu.get_state()
+    hg = gpu.histogram(1)
+    xs = st["xs"]
+    limits = orc.min_max(xs, 100, 8192)
+    assert np.array_equal(hg.limits.reshape(-1), limits)
+    counts = orc.histogram_counts(xs, 100, 8192, G.WGS, limits).reshape(100, G.WGS)
+    assert np.array_equal(gpu.histogram_counts(), counts)
+    m, v = orc.mean_variance(xs, 100, 8192)
+    assert np.allclose(gpu.mean(), m, rtol=1e-5, atol=1e-5)
+    assert np.allclose(gpu.variance(), v, rtol=1e-5)
+    assert np.allclose(gpu.sd(), np.sqrt(v), rtol=1e-5)
+
+
+def test_dataset_engine_reference_case(factory):
+    """T/core_test.clj:18-30: 22 x (31*2^16) random matrix; histogram integrates to 1, moments match."""
+    n, m = 31 * 2 ** 16, 22
+    rng = np.random.default_rng(7)
+    data = rng.random((n, m), dtype=np.float32)
+    ds = factory.dataset_engine()
+    h, counts = ds.histogram(data, with_counts=True)
+    assert abs(float(h.pdf[4].sum()) / G.WGS - 1.0) < 1e-3            # the reference's own check (limits ~ [0,1])
+    lim = orc.min_max(data, m, n)
+    assert np.array_equal(h.limits.reshape(-1), lim)
+    want = orc.histogram_counts(data, m, n, G.WGS, lim).reshape(m, G.WGS)
+    assert np.array_equal(counts, want)
+    mean, var = ds.data_mean(data), ds.data_variance(data)
+    assert abs(float((data.astype(np.float64).mean(axis=0) - mean).sum())) < 0.003
+    assert abs(float((data.astype(np.float64).var(axis=0) - var).sum())) < 0.003
+    om, ov = orc.mean_variance(data, m, n)
+    assert np.allclose(mean, om, rtol=1e-6) and np.allclose(var, ov, rtol=1e-5)
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (3, 2), (257, 5), (1000, 33)])
+def test_dataset_engine_ragged_shapes(factory, n, m):
+    rng = np.random.default_rng(n * 31 + m)
+    data = (rng.standard_normal((n, m)) * 3 + 1).astype(np.float32)
+    ds = factory.dataset_engine()
+    om, ov = orc.mean_variance(data, m, n)
+    assert np.allclose(ds.data_mean(data), om, rtol=1e-5, atol=1e-6)
+    assert np.allclose(ds.data_variance(data), ov, rtol=1e-4, atol=1e-6)
+    if n > 1:
+        h, counts = ds.histogram(data, with_counts=True)
+        lim = orc.min_max(data, m, n)
+        assert np.array_equal(h.limits.reshape(-1), lim)
+        assert np.array_equal(counts, orc.histogram_counts(data, m, n, G.WGS, lim).reshape(m, G.WGS))
+
+
+# ------------------------------------------------------------------------- statistical end-to-end --
+def test_beta_binomial_posterior_matches_analytic(factory):
+    """configs[1]: Beta(3,2) prior, N=50, z=15 -> Beta(18,37) (nvidia_gtx_test.clj:135-151) via mix!."""
+    from scipy import stats
+    model = models.beta_binomial_posterior()
+    params = np.concatenate([models.binomial_lik_params(50, 15), models.beta_params(3, 2)])
+    sf = factory.mcmc_factory(model)
+    s = sf.create_sampler(1234, 2 ** 16, params)
+    s.init_position(4321, f32([0, 1]))
+    tuned = mcmc.mix(s)
+    assert 0.2 <= tuned["acc-rate"] <= 0.75
+    x = s.sample()[:, 0].astype(np.float64)
+    post = stats.beta(18, 37)
+    assert abs(x.mean() - post.mean()) < 0.01 * post.mean()           # T/library_test.clj: within 1 %
+    assert abs(x.std() - post.std()) < 0.02 * post.std()
+    assert stats.kstest(x[::16], post.cdf).statistic < 0.03
+    h = s.histogram(4)
+    centers = h.limits[0, 0] + (np.arange(G.WGS) + 0.5) * (h.limits[0, 1] - h.limits[0, 0]) / G.WGS
+    assert np.abs(h.pdf[0] - post.pdf(centers)).max() < 0.35          # density-normalised histogram vs analytic pdf
+
+
+def test_mvn_moments_after_burn_in(factory):
+    d = 8
+    model = models.mvn_model(d)
+    params, mu, sigma = models.mvn_params(d, seed=5)
+    sf = factory.mcmc_factory(model)
+    s = sf.create_sampler(42, 2 ** 15, params)
+    s.init_position(43, f32([[-30, 30]] * d))
+    mcmc.mix(s)
+    s.burn_in(300, 2.0)
+    x = s.sample().astype(np.float64)
+    assert np.abs(x.mean(axis=0) - mu).max() < 0.25
+    assert np.allclose(np.cov(x.T), sigma, rtol=0.15, atol=0.5)
+
+
+# ----------------------------------------------------------------------------------- errors / misc --
+def test_walker_count_error(factory):
+    sf = factory.mcmc_factory(models.GAUSSIAN)
+    with pytest.raises(bb.WalkerCountError, match=r"Number of walkers \(300\) must be a multiple of 512\."):
+        sf.create_sampler(1, 300, f32([0, 1]))
+
+
+def test_state_roundtrip_and_init_position_from(factory):
+    sf, gpu, cpu = make_pair(factory, models.GAUSSIAN, 1, 1024, f32([0, 1]), f32([-3, 3]))
+    gpu.burn_in(10)
+    st = gpu.get_state()
+    other = sf.create_sampler(1, 1024, f32([0, 1]))
+    other.init_position(gpu)
+    st2 = other.get_state()
+    assert np.array_equal(st["xs"], st2["xs"]) and logpdf_close(st["logfn"], st2["logfn"]).all()
+    other.set_state(bare_seed=st["bare_seed"], move_seed=st["move_seed"], bare_counter=st["bare_counter"])
+    gpu.burn_in(5)
+    other.burn_in(5)
+    assert np.array_equal(gpu.get_state()["xs"], other.get_state()["xs"])
+
+
+def test_sample_small_n_and_processing_elements(factory):
+    sf, gpu, cpu = make_pair(factory, models.UNIFORM, 9, 1024, f32([-1, 2]), f32([-1, 2]))
+    assert np.array_equal(gpu.sample(10), cpu.sample(10))
+    assert factory.processing_elements() % G.WGS == 0 and factory.processing_elements() >= 100 * G.WGS
+    assert bb.launch_count() > 0

@@ -1,0 +1,159 @@
+"""Pin the CPU oracle on every golden vector the reference's tests hold for the hot path
+(SURVEY §8c).  CPU only; these are the tests that make the oracle trustworthy."""
+import numpy as np
+import pytest
+
+import goldens as G
+from bayadera_b200 import models
+from oracle import oracle as orc
+
+
+def f32(x):
+    return np.asarray(x, dtype=np.float32)
+
+
+@pytest.mark.parametrize("ctr,key,out", G.PHILOX_KATS)
+def test_philox_kat(ctr, key, out):
+    assert tuple(int(v) for v in orc.philox(ctr, key)) == out
+
+
+def test_direct_uniform_goldens():
+    g = G.DIRECT_UNIFORM
+    x = orc.direct_uniform(g["n"], G.SEED, *[float(np.float32(p)) for p in g["params"]])
+    assert np.array_equal(x[:4], f32(g["first4"]))
+    assert np.array_equal(x[-4:], f32(g["last4"]))
+    assert x.max() == np.float32(g["max"]) and x.min() == np.float32(g["min"])
+    assert abs(float(x.astype(np.float64).mean()) - g["mean"]) < 1e-4
+
+
+def uniform_sampler():
+    s = orc.OracleStretch(models.UNIFORM, G.SEED, G.W, f32([-1, 2]), wgs=G.WGS)
+    s.init(G.SEED)
+    s.init_position(G.SEED, f32([-1, 2]))
+    return s
+
+
+def test_uniform_stretch_positions_bit_exact():
+    s = uniform_sampler()
+    for want in G.UNIFORM_SAMPLES:
+        got = s.sample()[:4, 0]
+        assert np.array_equal(got, f32(want)), (got, want)
+
+
+def test_uniform_accu_step_block_sums_accept_counts():
+    s = uniform_sampler()
+    s.move_bare()
+    assert np.array_equal(s.xs[:4], f32(G.UNIFORM_SAMPLES[0]))
+    s.move_bare()
+    assert np.array_equal(s.xs[:4], f32(G.UNIFORM_SAMPLES[1]))
+    # raw accu launch of the reference test: seeds (123, 124), step 0 => move_seed must become 123
+    s.move_seed = G.SEED - 2
+    s.init_move(G.A)
+    s.move()
+    assert np.array_equal(s.xs[:4], f32(G.UNIFORM_ACCU_XS))
+    assert tuple(int(v) for v in s.accept[:10]) == G.UNIFORM_ACCU_ACCEPT
+    assert np.array_equal(s.blk_sums[:10], f32(G.UNIFORM_ACCU_BLOCK_SUMS))
+    assert abs(float(s.blk_sums.astype(np.float64).sum()) - G.UNIFORM_ACCU_TOTAL) < 2e-3
+    # ensemble mean of the step = total / W
+    assert abs(float(s.means[0][0]) - G.UNIFORM_ACCU_TOTAL / G.W) < 1e-6
+
+
+def test_block_tree_sum_matches_pairwise_definition():
+    rng = np.random.default_rng(0)
+    for n in (256, 255, 67, 1, 2, 3):
+        v = rng.standard_normal(n).astype(np.float32)
+        w = v.copy()
+        i = n
+        while i > 1:
+            odd = i & 1
+            i >>= 1
+            w[:i] = w[:i] + w[i:2 * i]
+            if odd:
+                w[i - 1] = w[i - 1] + w[2 * i]
+        assert orc.block_tree_sum(v) == float(w[0])
+
+
+def gaussian_sampler(seed_init):
+    s = orc.OracleStretch(models.GAUSSIAN, G.SEED, G.W, f32([3, 1.0]), wgs=G.WGS)
+    return s
+
+
+def test_gaussian_stretch_positions_bit_exact():
+    s = gaussian_sampler(G.SEED)
+    s.init(G.SEED)
+    s.init_position(G.SEED, f32([-7, 7]))
+    for want in G.GAUSSIAN_SAMPLES:
+        got = s.sample()[:4, 0]
+        assert np.array_equal(got, f32(want)), (got, want)
+
+
+def test_gaussian_burn_in_summary():
+    s = gaussian_sampler(G.SEED)
+    s.init_position(G.SEED, f32([-7, 7]))
+    s.init(G.SEED + 1)
+    s.burn_in(100, 1.5)
+    x = s.sample()[:, 0]
+    # the reference's two backends disagree at ~2e-4 here (fast-math exp); so may the oracle
+    for ref in (G.BURN_IN_CUDA, G.BURN_IN_OPENCL):
+        assert abs(float(x.astype(np.float64).mean()) - ref["mean"]) < 2e-3
+    x2 = s.sample()[:, 0]
+    strided = x2[::1500]
+    assert strided.size == 8
+    assert np.allclose(strided, f32(G.BURN_IN_CUDA["strided"]), atol=5e-3)
+    x3 = s.sample()[:, 0]
+    assert abs(float(x3.astype(np.float64).std()) - G.BURN_IN_CUDA["sd"]) < 2e-3
+
+
+def test_acc_rate_and_tau_statistical():
+    s = orc.OracleStretch(models.GAUSSIAN, G.SEED, 2 * G.W, f32([200, 1]), wgs=G.WGS)
+    s.init(G.SEED)
+    s.init_position(G.SEED, f32([180.0, 220.0]))
+    s.burn_in(5120, 8.0)
+    acc = s.acc_rate(8.0)
+    assert abs(acc - G.ACC_RATE_OPENCL) < 1.5e-3, acc
+    # the CUDA test's run length (nvidia_gtx_test.clj:318); the 3670-step OpenCL variant uses a
+    # different acor kernel and is too noisy to pin on
+    res = s.run_sampler(63670, 8.0)
+    assert abs(float(res["autocorrelation"]["tau"][0]) - G.TAU) < 0.5
+    assert 0.48 < res["acceptance-rate"] < 0.49
+
+
+@pytest.mark.parametrize("n", [67, 367, 112640])
+def test_acor_fixtures(n):
+    series = G.acor_fixture(n)
+    tau, mean, sigma, lag = orc.acor(series, 2, n, G.WGS)
+    want = G.ACOR[n]
+    if n == 112640:
+        assert abs(float(tau[1]) - want["tau"]) < 1e-3
+        assert abs(float(sigma[0]) - want["sigma"]) < 1e-3
+    else:
+        assert np.allclose(tau, want["tau"], rtol=2e-6), tau
+        assert abs(float(sigma[0]) - want["sigma"]) < 2e-6 * want["sigma"] + 1e-7
+
+
+def test_acor_too_short_raises():
+    with pytest.raises(ValueError, match="autocorrelation time is too long"):
+        orc.acor(np.zeros((40, 1), dtype=np.float32), 1, 40, G.WGS)
+
+
+def test_histogram_pipeline_properties():
+    rng = np.random.default_rng(1)
+    n, dim, wgs = 4096, 3, 256
+    data = rng.random((n, dim)).astype(np.float32)
+    limits = orc.min_max(data, dim, n)
+    assert np.array_equal(limits.reshape(dim, 2)[:, 0], data.min(axis=0))
+    assert np.array_equal(limits.reshape(dim, 2)[:, 1], data.max(axis=0))
+    counts = orc.histogram_counts(data, dim, n, wgs, limits)
+    assert counts.reshape(dim, wgs).sum(axis=1).tolist() == [n] * dim
+    pdf = orc.uint_to_real(counts, dim, wgs, n, limits).reshape(dim, wgs)
+    widths = (limits.reshape(dim, 2)[:, 1] - limits.reshape(dim, 2)[:, 0]) / wgs
+    assert np.allclose((pdf * widths[:, None]).sum(axis=1), 1.0, atol=1e-5)   # T/core_test.clj:24-25
+    ranks = orc.bin_ranks(pdf.reshape(-1), dim, wgs).reshape(dim, wgs).astype(int)
+    for d in range(dim):
+        assert sorted(ranks[d].tolist()) == list(range(wgs))
+        assert np.all(np.diff(pdf[d][ranks[d]]) <= 0)                            # decreasing mass
+
+
+def test_walker_count_check():
+    with pytest.raises(ValueError, match="must be a multiple of 512"):
+        orc.OracleStretch(models.GAUSSIAN, 1, 300, f32([0, 1]), wgs=256)
