@@ -385,7 +385,9 @@ __global__ void k_acor(uint32_t dim, uint32_t n, uint32_t wgs, uint32_t lag, uin
     __syncthreads();
 
     uint32_t lag2 = lag, n2 = n, stride = 1;
-    float c0 = 0.f, dv = 0.f, tau_d = 0.f;
+    // c0: first level's (used by the final tau, acor.cu:160); c0_prev: the previous level's, which the
+    // reference's loop body re-declares and divides the new level's d by (acor.cu:147, 156).
+    float c0 = 0.f, c0_prev = 0.f, dv = 0.f, tau_d = 0.f;
     bool first = true;
     while (true) {
         const uint32_t blk = wgs < n2 ? wgs : n2;
@@ -405,8 +407,9 @@ __global__ void k_acor(uint32_t dim, uint32_t n, uint32_t wgs, uint32_t lag, uin
         }
         const float c0v = (float)block_sum_d(pc0, sm);
         dv = (float)block_sum_d(pd, sm2);
-        if (first) { c0 = c0v; first = false; }
-        tau_d = dv / c0;
+        if (first) { c0 = c0v; c0_prev = c0v; first = false; }
+        tau_d = dv / c0_prev;
+        c0_prev = c0v;
         if (!((min_lag < lag2) && ((float)lag2 < tau_d * (float)win_mult))) break;
         n2 /= 2;
         lag2 = (lag * win_mult < n2) ? lag : max(10u, n2 / win_mult);

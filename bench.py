@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py — walker-steps/s of the stretch-move hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c5] [--impl b200|reference]
+
+One bench "step" = `moves_per_step` calls of move-bare! (odd + even half-ensemble launch each) over the whole
+ensemble, i.e. W * moves_per_step walker-steps (= logpdf evaluations).  Timed on the device with CUDA events on
+the engine's stream; L2 is flushed (256 MiB write) between timed steps; SM clocks and throttle reasons are
+sampled through NVML during the timed region.  `value` has the ensemble resident in HBM; `e2e` goes through the
+C-ABI with HOST buffers (ensemble uploaded from pinned memory, advanced, downloaded) inside the timed region.
+
+--impl reference times the CPU oracle (oracle/, the C restatement of the reference's kernels — the reference's
+own OpenCL/CUDA-JIT kernels cannot run here: no JVM, no POCL) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "walker-steps/sec"
+UNIT = "walker-steps/s"
+
+
+def f32(v):
+    return np.asarray(v, dtype=np.float32)
+
+
+# ------------------------------------------------------------------------------------------ workloads --
+def workload(name: str):
+    """BASELINE.json configs (SURVEY §8d synthetic inputs).  Returns a dict describing the job."""
+    from bayadera_b200 import models
+    if name == "c1":
+        return dict(key="c1", desc="1-D Gaussian(0,1), 2^14 walkers (BASELINE configs[0])", model=models.GAUSSIAN,
+                    params=f32([0, 1]), limits=f32([-7, 7]), walkers=2 ** 14, moves=256, a=2.0,
+                    cpu_walkers=2 ** 14)
+    if name == "c2":
+        params = np.concatenate([models.binomial_lik_params(50, 15), models.beta_params(3, 2)])
+        return dict(key="c2", desc="beta-binomial coin posterior, 2^18 walkers (BASELINE configs[1])",
+                    model=models.beta_binomial_posterior(), params=params, limits=f32([0, 1]), walkers=2 ** 18,
+                    moves=128, a=2.0, cpu_walkers=2 ** 16)
+    if name == "c3":
+        m = models.therapeutic_touch_model()
+        return dict(key="c3", desc="hierarchical therapeutic-touch, D=30, 280 trials, 2^16 walkers (BASELINE configs[2])",
+                    model=m, params=models.therapeutic_touch_data(), limits=m.limits_array(), walkers=2 ** 16,
+                    moves=32, a=2.0, cpu_walkers=2 ** 13)
+    if name == "c5":
+        m = models.mvn_model(100)
+        return dict(key="c5", desc="100-D correlated Gaussian, 2^20 walkers (BASELINE configs[4])", model=m,
+                    params=models.mvn_params(100)[0], limits=m.limits_array(), walkers=2 ** 20, moves=4, a=1.25,
+                    cpu_walkers=2 ** 11)
+    raise SystemExit(f"unknown workload {name}")
+
+
+def algorithmic_bytes_per_walker_step(dim: int, p_acc: float) -> float:
+    """4(2D+1) read + 4(D+1) p_acc written."""
+    return 4.0 * (2 * dim + 1) + 4.0 * (dim + 1) * p_acc
+
+
+# --------------------------------------------------------------------------------------------- clocks --
+class ClockSampler(threading.Thread):
+    """Samples SM clock and clock-event reasons through NVML every 100 ms while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def finish(self) -> dict:
+        self._stop.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ reference --
+def cpu_rate(wl: dict, budget_s: float, walkers: int):
+    """walker-steps/s of the CPU oracle (all host threads) on a bounded sample of the workload."""
+    from oracle import oracle as orc
+    s = orc.OracleStretch(wl["model"], 123, walkers, wl["params"], wgs=256)
+    s.init_position(123, wl["limits"])
+    s.a_bare = wl["a"]
+    s.move_bare()                                   # warm-up + calibration
+    t0 = time.perf_counter()
+    s.move_bare()
+    per_move = max(time.perf_counter() - t0, 1e-6)
+    n = int(max(2, min(10000, budget_s / per_move)))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        s.move_bare()
+    dt = time.perf_counter() - t0
+    return walkers * n / dt, n, dt, orc.lib().orc_num_threads()
+
+
+def run_reference(args, wl: dict, rank: int, world: int):
+    if rank != 0:
+        return
+    walkers = wl["cpu_walkers"]
+    budget = 4.0
+    for _ in range(args.warmup):
+        cpu_rate(wl, 0.2, walkers)
+    rates, total_t = [], 0.0
+    for _ in range(args.steps):
+        r, n, dt, threads = cpu_rate(wl, budget, walkers)
+        rates.append(r)
+        total_t += dt
+    value = float(np.mean(rates))
+    sample = f"{walkers} walkers x ~{n} moves per step ({budget:.0f} s budget) of workload {wl['key']}"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "walkers": walkers, "dim": wl["model"].dimension,
+                       "engine": "CPU oracle (C restatement of the reference kernels, OpenMP over walkers)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- main --
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("BAY_WORKLOAD", "c2"))
+    ap.add_argument("--moves-per-step", type=int, default=0)
+    ap.add_argument("--walkers", type=int, default=0)
+    ap.add_argument("--wgs", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl = workload(args.workload)
+    if args.walkers:
+        wl["walkers"] = args.walkers
+    if args.moves_per_step:
+        wl["moves"] = args.moves_per_step
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import bayadera_b200 as bb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: bayadera_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W, D, M, a, model = wl["walkers"], wl["model"].dimension, wl["moves"], wl["a"], wl["model"]
+    stream = torch.cuda.current_stream()
+    factory = bb.B200BayaderaFactory(device=local_rank, stream=stream.cuda_stream, wgs=args.wgs)
+    sfactory = factory.mcmc_factory(model)
+    sampler = sfactory.create_sampler(123 + rank, W, wl["params"])
+    sampler.init_position(1000 + rank, wl["limits"])
+    sampler.burn_in(max(64, M), a)                      # leave the initial box before timing
+    p_acc = sampler.acc_rate(a)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    for _ in range(args.warmup):
+        sampler.burn_in(M, a)
+    barrier()
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = bb.launch_count()
+    barrier()
+    for s_ev, e_ev in ev:
+        flush.fill_(1)                                  # evict the ensemble from L2 between timed steps
+        s_ev.record(stream)
+        sampler.burn_in(M, a)
+        e_ev.record(stream)
+    barrier()
+    launches = bb.launch_count() - launches0
+    clk = clocks.finish()
+    dev_ms = sum(s.elapsed_time(e) for s, e in ev)
+
+    # ---- e2e: host ensemble -> device, advance, device -> host, through the C-ABI ----
+    state = sampler.get_state()
+    xs_host = torch.from_numpy(state["xs"]).pin_memory().numpy()
+    lp_host = torch.from_numpy(state["logfn"]).pin_memory().numpy()
+    sampler.set_state(xs=xs_host, logfn=lp_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sampler.set_state(xs=xs_host, logfn=lp_host)
+        sampler.burn_in(M, a)
+        out = sampler.get_state()
+        xs_host[:] = out["xs"]
+        lp_host[:] = out["logfn"]
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    total_ws = float(world) * W * M * args.steps
+    value = total_ws / (dev_ms * 1e-3)
+    e2e_value = total_ws / (e2e_ms * 1e-3)
+    per_launch_ms = dev_ms / (2.0 * M * args.steps)
+    bytes_per_launch = (W / 2) * algorithmic_bytes_per_walker_step(D, p_acc)
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            r, n, dt, threads = cpu_rate(wl, 12.0, wl["cpu_walkers"])
+            cpu = {"value": r, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{wl['cpu_walkers']} walkers x {n} moves ({dt:.1f} s) of workload {wl['key']}, CPU oracle (OpenMP)"}
+        info = sfactory.kernel_info("bay_stretch_bare")
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["desc"], "walkers_per_gpu": W, "dim": D, "moves_per_step": M, "a": a,
+                           "acceptance": round(p_acc, 4), "wgs": args.wgs,
+                           "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (no exchange)",
+                           "l2": "flushed between timed steps (256 MiB write)",
+                           "kernel": {"name": "bay_stretch_bare", **info}},
+                "e2e": {"value": e2e_value, "unit": UNIT,
+                        "h2d_bytes_per_step": int(xs_host.nbytes + lp_host.nbytes),
+                        "d2h_bytes_per_step": int(xs_host.nbytes + lp_host.nbytes),
+                        "what": "bay_set_state(host ensemble) + burn-in! + bay_get_state(host) per step"},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "kernel": "bay_stretch_bare", "peak_source": peak_src,
+                             "bytes_per_launch": bytes_per_launch, "launch_us": per_launch_ms * 1e3},
+                "cpu_baseline": cpu, "clocks": clk}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -424,8 +424,11 @@ int orc_acor(uint32_t dim, uint32_t n, uint32_t wgs, float *series,
                 series[(size_t)(2 * g) * stride * dim + d] +=
                     series[(size_t)(2 * g + 1) * stride * dim + d];
             stride *= 2;
+            /* acor.cu:147 re-declares c0 inside the loop body (= c0acc of the PREVIOUS level),
+             * and acor.cu:156 divides the new level's d by that shadowing value. */
+            const float c0_prev = c0v;
             acor_pass(n2, wgs, stride * dim, d, lag2, series, &c0v, &dv);
-            tau_d = dv / c0;
+            tau_d = dv / c0_prev;
         }
         const float scale = (float)stride * (float)(n2 - lag2);
         tau[d] = dv * (float)(n - lag) / (scale * c0);
