@@ -74,7 +74,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.max_mhz, self._stop = index, [], set(), None, threading.Event()
+        self.index, self.samples, self.reasons, self.max_mhz, self._halt = index, [], set(), None, threading.Event()
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -87,7 +87,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         if self.nv is None:
             return
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
                 try:
@@ -99,10 +99,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._halt.wait(0.1)
 
     def finish(self) -> dict:
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
@@ -197,8 +197,12 @@ def main():
         torch.cuda.synchronize()
 
     W, D, M, a, model = wl["walkers"], wl["model"].dimension, wl["moves"], wl["a"], wl["model"]
-    stream = torch.cuda.current_stream()
+    # an explicit (non-default) stream: the engine enqueues on it and the timing events are recorded on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     factory = bb.B200BayaderaFactory(device=local_rank, stream=stream.cuda_stream, wgs=args.wgs)
+    assert factory.stream() == stream.cuda_stream
     sfactory = factory.mcmc_factory(model)
     sampler = sfactory.create_sampler(123 + rank, W, wl["params"])
     sampler.init_position(1000 + rank, wl["limits"])

@@ -182,7 +182,7 @@ def check_steplocked(gpu, cpu, steps, a, beta_t=1.0, tie_tol=TIE_TOL):
             mism_total += int((~same_pos).sum())
             agree_acc = same_pos & acc_cpu
             assert logpdf_close(glp[sl][agree_acc], cpu.lp[sl][agree_acc]).all(), "accepted log-density parity"
-            assert np.array_equal(glp[sl][same_pos & ~acc_cpu], before_lp[sl][same_pos & ~acc_cpu])
+            assert np.array_equal(glp[sl][same_pos & ~acc_cpu], before_lp[sl][same_pos & ~acc_cpu], equal_nan=True)
             del moved_gpu
         cpu.bare_counter += 1
     assert mism_total <= max(2, int(2e-4 * steps * 2 * H)), f"too many near-tie mismatches: {mism_total}"
