@@ -30,6 +30,9 @@
 static const char* kStretchProgram =
 #include "stretch_program.inc"
     ;
+static const char* kGlmProgram =
+#include "glm_program.inc"
+    ;
 
 // jitify-style stub so that `#include <stdint.h>` inside model sources resolves under NVRTC
 // (the reference ships the same kind of stub, G/:647).
@@ -232,6 +235,9 @@ struct bay_model {
     bay_engine* e = nullptr;
     CUmodule mod = nullptr;
     CUfunction f_bare = nullptr, f_accu = nullptr, f_logfn = nullptr;
+    // GLM (row-additive Bernoulli-logit) path, present iff `glm`
+    CUfunction f_glm_propose = nullptr, f_glm_loglik = nullptr, f_glm_lp_init = nullptr, f_glm_accept = nullptr;
+    bool glm = false;
     int dim = 1, params_size = 0;
     uint32_t flags = 0;
     int block = 128;  // bare/logfn block size
@@ -259,6 +265,17 @@ struct bay_sampler {
     float* ranks = nullptr;                   // wgs x D
     double* macc = nullptr;                   // D x 2
     float* vec_d = nullptr;                   // 4 x D scratch
+    // GLM path: repacked dataset, proposals and double-precision log-densities
+    uint64_t glm_rows = 0;                    // local rows (this rank's shard)
+    float* glm_x = nullptr;                   // rows x D row-major
+    double* glm_sy = nullptr;                 // D: X^T y (all-reduced over row shards)
+    float* glm_yt = nullptr;                  // D x W proposals / points, SoA
+    float* glm_z = nullptr;                   // H
+    float* glm_u = nullptr;                   // H
+    double* glm_partial = nullptr;            // chunks x W
+    double* glm_sp = nullptr;                 // W: sum_rows softplus
+    double* lp64 = nullptr;                   // W
+    uint32_t glm_chunks = 0, glm_rows_per_chunk = 0;
     // host-side counters: G/:282-287, 340-400
     int32_t bare_seed = 0, move_seed = 0;
     uint32_t bare_counter = 0, move_counter = 0;
@@ -371,6 +388,7 @@ static int nvrtc_build(const char* const* srcs, int nsrc, const char* logfn_name
         src += "\n";
     }
     src += kStretchProgram;
+    if ((flags & BAY_MODEL_GLM_LOGISTIC) && dim % 4 == 0) src += kGlmProgram;
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-default-device", "-lineinfo", "--std=c++17",
                                      "-DREAL=float", "-DREAL2=float2", "-DACCUMULATOR=float",
                                      "-DLOGFN=" + std::string(logfn_name), "-DDIM=" + std::to_string(dim),
@@ -449,6 +467,20 @@ extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsr
             return cu_fail(cr, fn.name);
         }
     }
+    if ((flags & BAY_MODEL_GLM_LOGISTIC) && dim % 4 == 0) {
+        struct { const char* name; CUfunction* f; } gfns[] = {
+            {"bay_glm_propose", &m->f_glm_propose}, {"bay_glm_loglik", &m->f_glm_loglik},
+            {"bay_glm_lp_init", &m->f_glm_lp_init}, {"bay_glm_accept", &m->f_glm_accept}};
+        for (auto& fn : gfns) {
+            cr = g_cu.ModuleGetFunction(fn.f, m->mod, fn.name);
+            if (cr != CUDA_SUCCESS) {
+                g_cu.ModuleUnload(m->mod);
+                delete m;
+                return cu_fail(cr, fn.name);
+            }
+        }
+        m->glm = true;
+    }
     *out = m;
     return BAY_OK;
 }
@@ -489,6 +521,8 @@ static void stretch_coeffs(float a, float* cA, float* cB, float* cC) {
     *cB = 2.0f * o;
     *cC = inv;
 }
+
+#include "engine_glm.inc"
 
 static int sampler_alloc(bay_sampler* s) {
     const bay_engine* e = s->m->e;
@@ -553,6 +587,10 @@ extern "C" int bay_sampler_create(bay_model* m, int32_t seed, int64_t walkers, c
         return fail(BAY_ECUDA, "params upload failed: %s", cudaGetErrorString(ce));
     }
     s->own_params = true;
+    if (m->glm) {
+        int r = glm_setup(s);
+        if (r != BAY_OK) { bay_sampler_release(s); return r; }
+    }
     *out = s;
     return BAY_OK;
 }
@@ -563,6 +601,10 @@ extern "C" int bay_sampler_create_dev(bay_model* m, int32_t seed, int64_t walker
     TRY(sampler_create_common(m, seed, walkers, params_count, &s));
     s->params = reinterpret_cast<float*>(params_dev);
     s->own_params = false;
+    if (m->glm) {
+        int r = glm_setup(s);
+        if (r != BAY_OK) { bay_sampler_release(s); return r; }
+    }
     *out = s;
     return BAY_OK;
 }
@@ -572,6 +614,7 @@ extern "C" int bay_sampler_release(bay_sampler* s) {
     cudaSetDevice(s->m->e->device);
     cudaStreamSynchronize(s->m->e->stream);
     if (s->own_params) cudaFree(s->params);
+    glm_release(s);
     void* bufs[] = {s->xs, s->lp, s->accept, s->blk_sums, s->accept_total, s->means, s->hist_counts, s->mm,
                     s->limits, s->pdf, s->ranks, s->macc, s->vec_d};
     for (void* b : bufs) if (b) cudaFree(b);
@@ -592,6 +635,7 @@ extern "C" int bay_init(bay_sampler* s, int32_t seed) {
 
 static int launch_logfn_all(bay_sampler* s) {
     bay_model* m = s->m;
+    if (m->glm) return glm_logfn_all(s);
     uint32_t n = (uint32_t)s->W, pitch = (uint32_t)s->W;
     void* args[] = {&n, &s->data_len, &s->params_len, &s->params, &s->xs, &pitch, &s->lp};
     return launch(m->e, m->f_logfn, cdiv(n, m->block), m->block, args);
@@ -629,6 +673,7 @@ extern "C" int bay_init_position_from(bay_sampler* s, const bay_sampler* other) 
 static int half_bare(bay_sampler* s, int half, uint32_t seed, uint32_t tag, float cA, float cB, float cC,
                      float beta, uint32_t step) {
     bay_model* m = s->m;
+    if (m->glm) return glm_half(s, half, seed, tag, cA, cB, cC, beta, step, 0u);
     uint32_t K = (uint32_t)s->H, pitch = (uint32_t)s->W;
     float* act = s->xs + (half ? s->H : 0);
     float* cmp = s->xs + (half ? 0 : s->H);
@@ -641,6 +686,7 @@ static int half_bare(bay_sampler* s, int half, uint32_t seed, uint32_t tag, floa
 static int half_accu(bay_sampler* s, int half, uint32_t seed, uint32_t tag, float cA, float cB, float cC,
                      uint32_t step) {
     bay_model* m = s->m;
+    if (m->glm) return glm_half(s, half, seed, tag, cA, cB, cC, 1.0f, step, 1u);
     uint32_t K = (uint32_t)s->H, pitch = (uint32_t)s->W, accumulate = half ? 1u : 0u;
     float* act = s->xs + (half ? s->H : 0);
     float* cmp = s->xs + (half ? 0 : s->H);

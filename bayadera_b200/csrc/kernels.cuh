@@ -427,4 +427,44 @@ __global__ void k_acor(uint32_t dim, uint32_t n, uint32_t wgs, uint32_t lag, uin
     }
 }
 
+// ------------------------------------------------------ GLM data preparation --
+// Rows [y, x_1..x_D] (stride D+1, as the model packs them into `params`) are split once
+// into Xmat (rows x D row-major, 16-byte aligned rows for cp.async / TMA) and sy = X^T y.
+__global__ void k_glm_repack(const float* __restrict__ data, uint64_t rows, uint32_t dim,
+                             float* __restrict__ xmat) {
+    const uint64_t total = rows * dim;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const uint64_t r = e / dim;
+        const uint32_t i = (uint32_t)(e - r * dim);
+        xmat[e] = data[r * (dim + 1) + 1 + i];
+    }
+}
+
+// sy[i] += sum_r y_r * x_{r,i}; one CTA per row chunk, thread = dimension (dim <= blockDim.x),
+// double accumulation, one atomicAdd(double) per (chunk, dim).
+__global__ void k_glm_xty(const float* __restrict__ data, uint64_t rows, uint32_t dim,
+                          uint64_t rows_per_block, double* __restrict__ sy) {
+    const uint64_t r0 = (uint64_t)blockIdx.x * rows_per_block;
+    const uint64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    for (uint32_t i = threadIdx.x; i < dim; i += blockDim.x) {
+        double s = 0.0;
+        for (uint64_t r = r0; r < r1; r++) {
+            const float* row = data + r * (dim + 1);
+            s += (double)row[0] * (double)row[1 + i];
+        }
+        atomicAdd(&sy[i], s);
+    }
+}
+
+// sp[k] = sum over row chunks of partial[c*H + k], fixed order (deterministic)
+__global__ void k_glm_finish(uint32_t H, uint32_t chunks, const double* __restrict__ partial,
+                             double* __restrict__ sp) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= H) return;
+    double s = 0.0;
+    for (uint32_t c = 0; c < chunks; c++) s += partial[(size_t)c * H + k];
+    sp[k] = s;
+}
+
 }  // namespace bay

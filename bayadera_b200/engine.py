@@ -50,6 +50,21 @@ def _f32(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+@dataclass
+class DeviceParams:
+    """A params vector that already lives in device memory: raw pointer, element count and an object that
+    keeps the allocation alive (e.g. the torch tensor it came from)."""
+    ptr: int
+    count: int
+    owner: object = None
+
+    @staticmethod
+    def from_torch(t) -> "DeviceParams":
+        import torch
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        return DeviceParams(int(t.data_ptr()), int(t.numel()), t)
+
+
 class B200BayaderaFactory:
     """``gtx-bayadera-factory [ctx hstream compute-units WGS]`` (nvidia_gtx.clj:791-807).
 
@@ -151,9 +166,14 @@ class B200Stretch:
         self._L, self.sfactory = sfactory._L, sfactory
         self.model = sfactory.model
         self.DIM, self.WGS = self.model.dimension, sfactory.factory.wgs
-        p = _f32(params).reshape(-1)
         h = C.c_void_p()
-        check(self._L.bay_sampler_create(sfactory._h, seed, walkers, ptr(p), p.size, C.byref(h)))
+        if isinstance(params, DeviceParams):
+            # params already on the engine's device (the reference borrows a cuda-float vector, nvidia_gtx.clj:558)
+            self._params_keepalive = params
+            check(self._L.bay_sampler_create_dev(sfactory._h, seed, walkers, params.ptr, params.count, C.byref(h)))
+        else:
+            p = _f32(params).reshape(-1)
+            check(self._L.bay_sampler_create(sfactory._h, seed, walkers, ptr(p), p.size, C.byref(h)))
         self._h, self.walker_count = h, walkers
 
     # Info (nvidia_gtx.clj:332-335)

@@ -287,21 +287,25 @@ def logistic_regression_model(d: int = 64, prior_sd: float = 10.0) -> DeviceMode
 
     Row-additive + GLM metadata lets the engine run the tiled / tensor-core likelihood; the
     serial body below is the reference-style per-thread loop (and the oracle)."""
+    prior_body = f"""
+        REAL ss = 0.0f;
+        for (uint32_t i = 0; i < {d}; i++) ss += x[i] * x[i];
+        return - params[0] * ss;"""
     body = f"""
         const uint32_t stride = {d + 1};
         const uint32_t rows = data_len / stride;
-        REAL acc = 0.0f;
+        double acc = 0.0;   /* 1e7 rows: the sum is ~ -5e6, beyond fp32 resolution */
         for (uint32_t r = 0; r < rows; r++) {{
-            const REAL* row = &params[r * stride];
+            const REAL* row = &params[(size_t)r * stride];
             REAL eta = 0.0f;
             for (uint32_t i = 0; i < {d}; i++) eta += row[1 + i] * x[i];
             const REAL sp = fmaxf(eta, 0.0f) + log(1.0f + exp(-fabsf(eta)));
-            acc += row[0] * eta - sp;
+            acc += (double)(row[0] * eta - sp);
         }}
-        REAL ss = 0.0f;
-        for (uint32_t i = 0; i < {d}; i++) ss += x[i] * x[i];
-        return acc - params[data_len] * ss;"""
-    src = distribution_source("logreg_mcmc_logpdf", body)
+        return (REAL)(acc + (double)logreg_prior(data_len, params_len, &params[data_len], dim, x));"""
+    # BAY_GLM_PRIOR names the prior for the engine's row-additive GLM path (glm_program.inc)
+    src = _wrap("#define BAY_GLM_PRIOR logreg_prior\n", _fn("logreg_prior", prior_body),
+                _fn("logreg_mcmc_logpdf", body))
     return DeviceModel("logreg", (src,), "logreg_mcmc_logpdf", d, 1, _lim(*([(-1.0, 1.0)] * d)),
                        "logreg_mcmc_logpdf", flags=FAST_MATH | ROW_ADDITIVE | GLM_LOGISTIC,
                        meta={"row_stride": d + 1, "prior_sd": prior_sd})

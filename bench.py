@@ -58,7 +58,37 @@ def workload(name: str):
         return dict(key="c5", desc="100-D correlated Gaussian, 2^20 walkers (BASELINE configs[4])", model=m,
                     params=models.mvn_params(100)[0], limits=m.limits_array(), walkers=2 ** 20, moves=4, a=1.25,
                     cpu_walkers=2 ** 11)
+    if name == "c4":
+        d, rows = 64, 10 ** 7
+        m = models.logistic_regression_model(d)
+        return dict(key="c4", desc="Bayesian logistic regression, D=64, 10^7 synthetic rows (BASELINE configs[3])",
+                    model=m, params=None, limits=m.limits_array(), walkers=1024, moves=1, a=1.2,
+                    cpu_walkers=512, rows=rows, cpu_rows=4000, glm=True)
     raise SystemExit(f"unknown workload {name}")
+
+
+def logreg_rows_host(rows: int, d: int, seed: int = 2024) -> np.ndarray:
+    """Synthetic c4 data (SURVEY §8d): X ~ N(0,1), theta* ~ N(0,1/8), y ~ Bernoulli(sigmoid(X theta*));
+    packed as the model expects: rows [y, x_1..x_d] followed by the hyper-parameter 1/(2*10^2)."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((rows, d), dtype=np.float32)
+    theta = (rng.standard_normal(d) / np.sqrt(8.0)).astype(np.float32)
+    y = (rng.random(rows) < 1.0 / (1.0 + np.exp(-(x @ theta)))).astype(np.float32)
+    return np.concatenate([np.concatenate([y[:, None], x], axis=1).reshape(-1), f32([1.0 / 200.0])])
+
+
+def logreg_rows_device(torch, rows: int, d: int, seed: int, device):
+    """Same distribution generated on the device (nothing shipped over PCIe for the 2.6 GB matrix)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty(rows * (d + 1) + 1, dtype=torch.float32, device=device)
+    mat = out[:-1].view(rows, d + 1)
+    mat[:, 1:].normal_(generator=g)
+    theta = torch.randn(d, generator=g, device=device) / (8.0 ** 0.5)
+    p = torch.sigmoid(mat[:, 1:] @ theta)
+    mat[:, 0] = (torch.rand(rows, generator=g, device=device) < p).float()
+    out[-1] = 1.0 / 200.0
+    return out
 
 
 def algorithmic_bytes_per_walker_step(dim: int, p_acc: float) -> float:
@@ -112,7 +142,10 @@ class ClockSampler(threading.Thread):
 def cpu_rate(wl: dict, budget_s: float, walkers: int):
     """walker-steps/s of the CPU oracle (all host threads) on a bounded sample of the workload."""
     from oracle import oracle as orc
-    s = orc.OracleStretch(wl["model"], 123, walkers, wl["params"], wgs=256)
+    params = wl["params"]
+    if params is None:                                # c4: bounded row sample, same generator family
+        params = logreg_rows_host(wl["cpu_rows"], wl["model"].dimension)
+    s = orc.OracleStretch(wl["model"], 123, walkers, params, wgs=256)
     s.init_position(123, wl["limits"])
     s.a_bare = wl["a"]
     s.move_bare()                                   # warm-up + calibration
@@ -124,7 +157,10 @@ def cpu_rate(wl: dict, budget_s: float, walkers: int):
     for _ in range(n):
         s.move_bare()
     dt = time.perf_counter() - t0
-    return walkers * n / dt, n, dt, orc.lib().orc_num_threads()
+    rate = walkers * n / dt
+    if wl.get("rows"):                                # cost is linear in the rows: extrapolate to the full dataset
+        rate *= wl["cpu_rows"] / wl["rows"]
+    return rate, n, dt, orc.lib().orc_num_threads()
 
 
 def run_reference(args, wl: dict, rank: int, world: int):
@@ -141,6 +177,8 @@ def run_reference(args, wl: dict, rank: int, world: int):
         total_t += dt
     value = float(np.mean(rates))
     sample = f"{walkers} walkers x ~{n} moves per step ({budget:.0f} s budget) of workload {wl['key']}"
+    if wl.get("rows"):
+        sample += f", on {wl['cpu_rows']} of {wl['rows']} rows, rate scaled linearly by rows"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -204,7 +242,10 @@ def main():
     factory = bb.B200BayaderaFactory(device=local_rank, stream=stream.cuda_stream, wgs=args.wgs)
     assert factory.stream() == stream.cuda_stream
     sfactory = factory.mcmc_factory(model)
-    sampler = sfactory.create_sampler(123 + rank, W, wl["params"])
+    params = wl["params"]
+    if params is None:
+        params = bb.DeviceParams.from_torch(logreg_rows_device(torch, wl["rows"], D, 2024, torch.device("cuda", local_rank)))
+    sampler = sfactory.create_sampler(123 + rank, W, params)
     sampler.init_position(1000 + rank, wl["limits"])
     sampler.burn_in(max(64, M), a)                      # leave the initial box before timing
     p_acc = sampler.acc_rate(a)
@@ -254,37 +295,54 @@ def main():
     value = total_ws / (dev_ms * 1e-3)
     e2e_value = total_ws / (e2e_ms * 1e-3)
     per_launch_ms = dev_ms / (2.0 * M * args.steps)
-    bytes_per_launch = (W / 2) * algorithmic_bytes_per_walker_step(D, p_acc)
     peaks_file = ROOT / "MEASURED_PEAKS.json"
-    if peaks_file.exists():
-        peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    peaks = json.loads(peaks_file.read_text()) if peaks_file.exists() else None
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    if wl.get("glm"):
+        # dominant kernel: the dataset likelihood (one launch per half-step; propose/finish/accept are ~1 % of it).
+        # Dense contraction X(rows x D) . Theta(D x H): 2*rows*D flops per walker-step, bf16-dense peak
+        # as the denominator (an fp32-accurate 3-term split can reach at most 1/3 of it).
+        kernel_name = "bay_glm_loglik"
+        flops_per_launch = 2.0 * wl["rows"] * D * (W / 2)
+        peak = float(peaks["bf16_tflops_sustained"]) if peaks else 1400.0
+        achieved = flops_per_launch / (per_launch_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "kernel": kernel_name, "peak_source": peak_src, "flops_per_launch": flops_per_launch,
+                "launch_us": per_launch_ms * 1e3,
+                "hbm_view": {"bytes_per_launch": 4.0 * wl["rows"] * D,
+                             "achieved_GBps": 4.0 * wl["rows"] * D / (per_launch_ms * 1e-3) / 1e9}}
     else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
+        kernel_name = "bay_stretch_bare"
+        bytes_per_launch = (W / 2) * algorithmic_bytes_per_walker_step(D, p_acc)
+        peak = float(peaks["hbm_gbs"]) if peaks else 6650.0
+        achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": kernel_name, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch,
+                "launch_us": per_launch_ms * 1e3}
 
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             r, n, dt, threads = cpu_rate(wl, 12.0, wl["cpu_walkers"])
             cpu = {"value": r, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"{wl['cpu_walkers']} walkers x {n} moves ({dt:.1f} s) of workload {wl['key']}, CPU oracle (OpenMP)"}
-        info = sfactory.kernel_info("bay_stretch_bare")
+                   "sample": f"{wl['cpu_walkers']} walkers x {n} moves ({dt:.1f} s) of workload {wl['key']}, CPU oracle (OpenMP)"
+                             + (f", on {wl['cpu_rows']} of {wl['rows']} rows, rate scaled linearly by rows" if wl.get("rows") else "")}
+        info = sfactory.kernel_info(kernel_name)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["desc"], "walkers_per_gpu": W, "dim": D, "moves_per_step": M, "a": a,
+                           **({"rows": wl["rows"]} if wl.get("rows") else {}),
                            "acceptance": round(p_acc, 4), "wgs": args.wgs,
                            "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (no exchange)",
                            "l2": "flushed between timed steps (256 MiB write)",
-                           "kernel": {"name": "bay_stretch_bare", **info}},
+                           "kernel": {"name": kernel_name, **info}},
                 "e2e": {"value": e2e_value, "unit": UNIT,
                         "h2d_bytes_per_step": int(xs_host.nbytes + lp_host.nbytes),
                         "d2h_bytes_per_step": int(xs_host.nbytes + lp_host.nbytes),
                         "what": "bay_set_state(host ensemble) + burn-in! + bay_get_state(host) per step"},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "bay_stretch_bare", "peak_source": peak_src,
-                             "bytes_per_launch": bytes_per_launch, "launch_us": per_launch_ms * 1e3},
+                "roofline": roof,
                 "cpu_baseline": cpu, "clocks": clk}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,0 +1,117 @@
+"""GPU parity of the GLM (Bernoulli-logit) row-additive likelihood path — BASELINE config 4's hot path.
+
+Oracle: the model's own serial LOGFN (double-accumulated row loop) run by the CPU oracle at sizes it finishes in
+seconds; at larger sizes, size-independent properties (row-shard additivity, equality with the generic per-thread
+path, permutation invariance over rows).  Tolerance (north_star): summed log-likelihood within 1e-5 relative.
+"""
+import dataclasses
+
+import numpy as np
+import pytest
+
+import bayadera_b200 as bb
+from bayadera_b200 import mcmc, models
+from oracle import oracle as orc
+from test_gpu_parity import check_steplocked, f32, logpdf_close
+
+pytestmark = pytest.mark.gpu
+WGS = 256
+
+
+@pytest.fixture(scope="module")
+def factory():
+    f = bb.B200BayaderaFactory(device=0, wgs=WGS)
+    yield f
+    f.release()
+
+
+def synth(rows, d, seed=2024):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((rows, d)).astype(np.float32)
+    theta = (rng.standard_normal(d) / np.sqrt(8)).astype(np.float32)
+    y = (rng.random(rows) < 1 / (1 + np.exp(-(x @ theta)))).astype(np.float32)
+    data = np.concatenate([y[:, None], x], axis=1).reshape(-1)
+    return np.concatenate([data, f32([1.0 / (2 * 10.0 ** 2)])]), theta
+
+
+@pytest.mark.parametrize("rows,d,walkers", [(1, 4, 512), (33, 8, 512), (5000, 64, 1024), (20011, 64, 512)])
+def test_glm_logdensity_matches_oracle(factory, rows, d, walkers):
+    model = models.logistic_regression_model(d)
+    params, _ = synth(rows, d)
+    sf = factory.mcmc_factory(model)
+    gpu = sf.create_sampler(5, walkers, params).init_position(6, model.limits_array())
+    cpu = orc.OracleStretch(model, 5, walkers, params, wgs=WGS).init_position(6, model.limits_array())
+    st = gpu.get_state()
+    assert np.array_equal(st["xs"].reshape(-1), cpu.xs)
+    assert logpdf_close(st["logfn"], cpu.lp, rtol=1e-5).all()
+
+
+def test_glm_steplocked_vs_oracle(factory):
+    model = models.logistic_regression_model(8)
+    params, _ = synth(700, 8)
+    sf = factory.mcmc_factory(model)
+    gpu = sf.create_sampler(9, 1024, params).init_position(10, model.limits_array())
+    cpu = orc.OracleStretch(model, 9, 1024, params, wgs=WGS).init_position(10, model.limits_array())
+    check_steplocked(gpu, cpu, steps=3, a=2.0, tie_tol=5e-3)
+
+
+def test_glm_equals_generic_path(factory):
+    """The tiled path and the reference-style per-thread serial loop must give the same chain statistics and the
+    same log-densities (1e-5 relative) — 'checked against the fp32 SIMT path'."""
+    d, rows, walkers = 16, 3000, 1024
+    glm = models.logistic_regression_model(d)
+    generic = dataclasses.replace(glm, flags=models.FAST_MATH)
+    params, theta = synth(rows, d)
+    a = factory.mcmc_factory(glm).create_sampler(1, walkers, params).init_position(2, glm.limits_array())
+    b = factory.mcmc_factory(generic).create_sampler(1, walkers, params).init_position(2, glm.limits_array())
+    sa, sb = a.get_state(), b.get_state()
+    assert np.array_equal(sa["xs"], sb["xs"])
+    assert logpdf_close(sa["logfn"], sb["logfn"], rtol=1e-5).all()
+    a.burn_in(3, 2.0)
+    b.burn_in(3, 2.0)
+    sa, sb = a.get_state(), b.get_state()
+    same = np.all(sa["xs"] == sb["xs"], axis=1)
+    assert same.mean() > 0.995                       # only near-tie accept flips may differ
+    assert logpdf_close(sa["logfn"][same], sb["logfn"][same], rtol=1e-5).all()
+
+
+def test_glm_row_shard_additivity_and_permutation(factory):
+    """Size-independent property at a larger size: log-likelihood over the rows = sum over row shards, and is
+    invariant under a permutation of the rows (prior counted once)."""
+    d, rows, walkers = 64, 200_000, 512
+    model = models.logistic_regression_model(d)
+    params, _ = synth(rows, d, seed=7)
+    data, hyper = params[:-1].reshape(rows, d + 1), params[-1:]
+    sf = factory.mcmc_factory(model)
+
+    def logdens(block):
+        p = np.concatenate([block.reshape(-1), hyper])
+        s = sf.create_sampler(3, walkers, p).init_position(4, model.limits_array())
+        out = s.get_state()
+        s.release()
+        return out["xs"], out["logfn"].astype(np.float64)
+
+    xs, full = logdens(data)
+    _, a = logdens(data[:70_001])
+    _, b = logdens(data[70_001:])
+    prior = -(float(hyper[0]) * (xs.astype(np.float64) ** 2).sum(axis=1))
+    assert np.allclose(full, a + b - prior, rtol=1e-5)
+    perm = np.random.default_rng(0).permutation(rows)
+    _, shuffled = logdens(data[perm])
+    assert np.allclose(full, shuffled, rtol=1e-6)
+
+
+def test_glm_posterior_recovers_truth(factory):
+    d, rows, walkers = 8, 20_000, 4096
+    model = models.logistic_regression_model(d)
+    params, theta = synth(rows, d, seed=11)
+    s = factory.mcmc_factory(model).create_sampler(21, walkers, params).init_position(22, model.limits_array())
+    mcmc.mix(s)
+    s.burn_in(200, 2.0)
+    res = s.run_sampler(64, 2.0)
+    assert 0.1 < res["acceptance-rate"] < 0.8
+    x = s.sample().astype(np.float64)
+    # posterior sd ~ 2/sqrt(rows) per coefficient; the posterior mean must sit within a few sd of the truth
+    assert np.abs(x.mean(axis=0) - theta).max() < 0.08
+    assert x.std(axis=0).max() < 0.05
+    assert np.all(np.isfinite(s.get_state()["logfn"]))
