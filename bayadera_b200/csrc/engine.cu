@@ -11,6 +11,7 @@
 // library loads — and reports BAY_ECUDA loudly — on a machine without a GPU.
 #include "../../include/bayadera_b200.h"
 #include "kernels.cuh"
+#include "kernels_glm_tc.cuh"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -22,6 +23,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -96,6 +98,9 @@ struct DriverApi {
     CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
     CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
     CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
     bool ok = false;
 };
 
@@ -155,7 +160,8 @@ int load_driver() {
               drv("cuFuncSetAttribute", &g_cu.FuncSetAttribute) &&
               drv("cuOccupancyMaxActiveBlocksPerMultiprocessor",
                   &g_cu.OccupancyMaxActiveBlocksPerMultiprocessor) &&
-              drv("cuGetErrorString", &g_cu.GetErrorString);
+              drv("cuGetErrorString", &g_cu.GetErrorString) &&
+              drv("cuTensorMapEncodeTiled", &g_cu.TensorMapEncodeTiled);
     if (!ok) return fail(BAY_ECUDA, "CUDA driver entry points unavailable (no NVIDIA driver / GPU?)");
     g_cu.ok = true;
     return BAY_OK;
@@ -276,6 +282,10 @@ struct bay_sampler {
     double* glm_sp = nullptr;                 // W: sum_rows softplus
     double* lp64 = nullptr;                   // W
     uint32_t glm_chunks = 0, glm_rows_per_chunk = 0;
+    // tensor-core variant (DIM == 64): bf16 hi/lo planes of the dataset and of the walker block + TMA maps
+    bool glm_tc = false;
+    __nv_bfloat16 *glm_xh = nullptr, *glm_xl = nullptr, *glm_ah = nullptr, *glm_al = nullptr;
+    CUtensorMap glm_map_xh, glm_map_xl;
     // host-side counters: G/:282-287, 340-400
     int32_t bare_seed = 0, move_seed = 0;
     uint32_t bare_counter = 0, move_counter = 0;

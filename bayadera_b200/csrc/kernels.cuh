@@ -467,4 +467,14 @@ __global__ void k_glm_finish(uint32_t H, uint32_t chunks, const double* __restri
     sp[k] = s;
 }
 
+// same with an explicit leading dimension of the partial matrix
+__global__ void k_glm_finish_ld(uint32_t n, uint32_t chunks, uint32_t ldp, const double* __restrict__ partial,
+                                double* __restrict__ sp) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double s = 0.0;
+    for (uint32_t c = 0; c < chunks; c++) s += partial[(size_t)c * ldp + k];
+    sp[k] = s;
+}
+
 }  // namespace bay

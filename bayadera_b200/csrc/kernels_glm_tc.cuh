@@ -1,0 +1,289 @@
+// bayadera_b200 — tensor-core (tcgen05 / TMEM / TMA, sm_100a) likelihood kernel of the GLM path.
+//
+// Computes, for up to 512 walkers per launch and ALL local dataset rows,
+//     sp[w] = sum_rows softplus( x_row . theta_w )
+// as the dense contraction  S(128 walkers x 128 rows) = Theta_blk(128 x 64) . X_tile(128 x 64)^T  on the
+// 5th-generation tensor cores, followed by a thread-local softplus reduction:
+//   * TMEM lanes = walkers, TMEM columns = dataset rows, so every epilogue thread owns one walker and sums
+//     over the columns it reads with tcgen05.ld — no cross-lane reduction at all.
+//   * fp32-level accuracy from bf16 inputs by a 3-term split (hi*hi + hi*lo + lo*hi), fp32 accumulation in TMEM:
+//     the dataset is split ONCE into (Xh, Xl) bf16 planes (same HBM bytes as the fp32 matrix), the walker block
+//     every half-step.  Dropped term lo*lo and split residuals are ~2^-16 relative per product, zero-mean.
+//   * Persistent, warp-specialised CTA (1 per SM): warp 8 = TMA producer (3-stage ring of 32 KB X tiles),
+//     warp 9 = TMEM allocator + single-thread MMA issuer (4 accumulator stages of 128 columns),
+//     warps 0-3 / 4-7 = two epilogue groups draining alternate accumulator stages.
+//   * softplus(e) = max(e,0) + log(1 + exp(-|e|)); the log is taken of a running PRODUCT of 64 factors (1+t),
+//     so the epilogue costs one MUFU.EX2 per element and one MUFU.LG2 per 64 (MUFU is the binding unit).
+// There is no counterpart in the reference (its LOGFN loops over the dataset serially in every thread,
+// e.g. K/cuda/distributions/gaussian.cu:40-42); the arithmetic contract is the oracle's serial model.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bay {
+namespace tc {
+
+constexpr int TILE = 128;                       // MMA M (walkers per block) and N (rows per tile)
+constexpr int KD = 64;                          // model dimension handled by this kernel
+constexpr int NSTAGE = 3;                       // X-tile ring
+constexpr int NACC = 4;                         // TMEM accumulator stages (4 x 128 columns = 512)
+constexpr int MAX_WB = 4;                       // walker blocks per launch (512 walkers)
+constexpr uint32_t TILE_BYTES = TILE * KD * 2;  // one bf16 plane of a tile: 16 KB
+constexpr int THREADS = 320;                    // 8 epilogue warps + TMA warp + MMA warp
+constexpr uint32_t IDESC =                      // kind::f16: D=f32, A=B=bf16, both K-major, N=128, M=128
+    (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+
+__host__ __device__ constexpr size_t smem_bytes(int nwb) {
+    return 1024 /*alignment slack*/ + (size_t)nwb * 2 * TILE_BYTES + (size_t)NSTAGE * 2 * TILE_BYTES + 256;
+}
+
+// ------------------------------------------------------------------ PTX helpers --
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+// K-major, SWIZZLE_128B operand tile (rows of 128 B, 8-row atoms of 1024 B): SBO = 1024 B, version 1, layout 2.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    const uint32_t lo = (smem_addr >> 4) & 0x3FFFu;
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+#define BAY_TMEM_LD32(r, taddr)                                                                              \
+    asm volatile(                                                                                            \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                            \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                            \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"            \
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),      \
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), \
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),          \
+          "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),          \
+          "=r"(r[30]), "=r"(r[31])                                                                           \
+        : "r"(taddr) : "memory")
+
+// ------------------------------------------------------------------ the kernel --
+// map_xh/map_xl: [rows][64] bf16 planes of the dataset; map_ah/map_al: [n_walkers][64] bf16 planes of the
+// walker block (hi, lo), origin at the first walker of this launch.  partial: [2*gridDim.x][ldp] doubles;
+// entry (2*cta + group, wb*128 + lane) = that epilogue thread's sum.
+template <int NWB>
+__global__ void __launch_bounds__(THREADS, 1)
+k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                const uint32_t rows, const uint32_t n_tiles, double* __restrict__ partial, const uint32_t ldp) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* a_hi = smem;                                   // NWB tiles
+    uint8_t* a_lo = a_hi + NWB * TILE_BYTES;                // NWB tiles
+    uint8_t* b_base = a_lo + NWB * TILE_BYTES;              // NSTAGE x (hi, lo)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + NSTAGE * 2 * TILE_BYTES);
+    uint64_t* full_bar = bars;                              // [NSTAGE] TMA -> MMA
+    uint64_t* empty_bar = bars + NSTAGE;                    // [NSTAGE] MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * NSTAGE;                // [NACC]   MMA -> epilogue
+    uint64_t* tempty_bar = bars + 2 * NSTAGE + NACC;        // [NACC]   epilogue -> MMA
+    uint64_t* a_bar = bars + 2 * NSTAGE + 2 * NACC;         // walker block landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2 * NACC + 1);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAGE; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < NACC; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        mbar_init(a_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) {   // TMEM: all 512 columns (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_expect_tx(a_bar, NWB * 2 * TILE_BYTES);
+            for (int wb = 0; wb < NWB; wb++) {
+                tma_load_2d(a_hi + wb * TILE_BYTES, &map_ah, 0, wb * TILE, a_bar);
+                tma_load_2d(a_lo + wb * TILE_BYTES, &map_al, 0, wb * TILE, a_bar);
+            }
+            for (uint32_t it = 0; it < my_tiles; it++) {
+                const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                mbar_expect_tx(&full_bar[s], 2 * TILE_BYTES);
+                const int row0 = (int)((blockIdx.x + it * gridDim.x) * TILE);
+                tma_load_2d(b_base + (2 * s) * TILE_BYTES, &map_xh, 0, row0, &full_bar[s]);
+                tma_load_2d(b_base + (2 * s + 1) * TILE_BYTES, &map_xl, 0, row0, &full_bar[s]);
+            }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            mbar_wait(a_bar, 0);
+            uint32_t item = 0;
+            for (uint32_t it = 0; it < my_tiles; it++) {
+                const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint64_t bh = make_desc(smem_u32(b_base + (2 * s) * TILE_BYTES));
+                const uint64_t bl = make_desc(smem_u32(b_base + (2 * s + 1) * TILE_BYTES));
+#pragma unroll
+                for (int wb = 0; wb < NWB; wb++, item++) {
+                    const uint32_t a = item % NACC, aph = (item / NACC) & 1u;
+                    mbar_wait(&tempty_bar[a], aph ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + a * TILE;
+                    const uint64_t ah = make_desc(smem_u32(a_hi + wb * TILE_BYTES));
+                    const uint64_t al = make_desc(smem_u32(a_lo + wb * TILE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, ah + 2 * k, bh + 2 * k, k > 0);   // hi*hi
+#pragma unroll
+                    for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, ah + 2 * k, bl + 2 * k, 1);       // hi*lo
+#pragma unroll
+                    for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, al + 2 * k, bh + 2 * k, 1);       // lo*hi
+                    tc_commit(&tfull_bar[a]);
+                }
+                tc_commit(&empty_bar[s]);   // the X tile is free once all MMAs that read it completed
+            }
+        }
+    } else {
+        // ===================== epilogue groups =====================
+        const uint32_t grp = warp >> 2;                  // 0: warps 0-3, 1: warps 4-7
+        const uint32_t quarter = warp & 3;               // TMEM lanes 32*quarter .. +31
+        double acc64[NWB];
+#pragma unroll
+        for (int wb = 0; wb < NWB; wb++) acc64[wb] = 0.0;
+        uint32_t item = 0;
+        for (uint32_t it = 0; it < my_tiles; it++) {
+            const uint32_t row0 = (blockIdx.x + it * gridDim.x) * TILE;
+            const uint32_t valid = min((uint32_t)TILE, rows - row0);
+#pragma unroll
+            for (int wb = 0; wb < NWB; wb++, item++) {
+                if ((item & 1u) != grp) continue;
+                const uint32_t a = item % NACC, aph = (item / NACC) & 1u;
+                mbar_wait(&tfull_bar[a], aph);
+                tc_fence_after();
+                float m = 0.f, lg = 0.f, p = 1.f;
+#pragma unroll
+                for (int c = 0; c < TILE / 32; c++) {
+                    uint32_t r[32];
+                    BAY_TMEM_LD32(r, tmem_base + ((quarter * 32u) << 16) + a * TILE + c * 32);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (valid == TILE) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float e = __uint_as_float(r[j]);
+                            const float t = ex2_approx(-fabsf(e) * 1.4426950408889634f);
+                            p = fmaf(p, t, p);
+                            m += fmaxf(e, 0.f);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            if ((uint32_t)(c * 32 + j) < valid) {
+                                const float e = __uint_as_float(r[j]);
+                                const float t = ex2_approx(-fabsf(e) * 1.4426950408889634f);
+                                p = fmaf(p, t, p);
+                                m += fmaxf(e, 0.f);
+                            }
+                        }
+                    }
+                    if (c & 1) { lg += lg2_approx(p); p = 1.f; }   // <= 2^64: no overflow
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[a]);
+                acc64[wb] += (double)fmaf(lg, 0.6931471805599453f, m);
+            }
+        }
+        const size_t base = (size_t)(2 * blockIdx.x + grp) * ldp + quarter * 32 + lane;
+#pragma unroll
+        for (int wb = 0; wb < NWB; wb++) partial[base + wb * TILE] = acc64[wb];
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// points (SoA, dim 64 x n, pitch) -> bf16 hi/lo planes [n][64] (row = walker), for the A operand
+__global__ void k_glm_split_points(const float* __restrict__ pts, uint32_t pitch, uint32_t n,
+                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;    // e = k*64 + i, coalesced stores
+    if (e >= n * KD) return;
+    const uint32_t k = e / KD, i = e % KD;
+    const float x = pts[(size_t)i * pitch + k];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi[e] = h;
+    lo[e] = __float2bfloat16_rn(x - __bfloat162float(h));
+}
+
+// dataset rows [y, x_1..x_64] (stride 65) -> bf16 hi/lo planes [rows][64]
+__global__ void k_glm_split_rows(const float* __restrict__ data, uint64_t rows,
+                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const uint64_t total = rows * KD;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const uint64_t r = e / KD;
+        const uint32_t i = (uint32_t)(e % KD);
+        const float x = data[r * (KD + 1) + 1 + i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        hi[e] = h;
+        lo[e] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+}
+
+}  // namespace tc
+}  // namespace bay

@@ -150,9 +150,10 @@ def test_init_logfn_and_steplocked_moves(factory, name, model, params, limits):
     check_steplocked(gpu, cpu, steps=6, a=2.0)
 
 
-def check_steplocked(gpu, cpu, steps, a, beta_t=1.0, tie_tol=TIE_TOL):
+def check_steplocked(gpu, cpu, steps, a, beta_t=1.0, tie_tol=TIE_TOL, exact_lp=True):
     """Per half-step: both engines start from the oracle's state; compare accept masks (modulo near-ties),
-    positions of agreeing walkers bit-for-bit and the accepted proposals' log-densities."""
+    positions of agreeing walkers bit-for-bit and the accepted proposals' log-densities.
+    exact_lp=False for GLM samplers, which recompute their (double) log-densities on set_state."""
     D, H = cpu.D, cpu.H
     cpu.a_bare = a
     cpu.set_temperature(beta_t)
@@ -171,8 +172,6 @@ def check_steplocked(gpu, cpu, steps, a, beta_t=1.0, tie_tol=TIE_TOL):
             other = slice((1 - half) * H, (2 - half) * H)
             assert np.array_equal(gx[other], cx[other]), "complementary half must be untouched"
             acc_cpu = cpu.diag["acc"].astype(bool)
-            moved_gpu = ~np.all(gx[sl] == before_x.reshape(-1, D)[sl], axis=1) | (glp[sl] != before_lp[sl])
-            # a GPU accept with Y == X bit-for-bit cannot be seen from outside; irrelevant for parity
             q, uz = cpu.diag["q"].astype(np.float64), cpu.diag["uz"].astype(np.float64)
             near_tie = np.abs(uz - q) <= tie_tol * np.maximum(q, 1e-30)
             same_pos = np.all(gx[sl] == cx[sl], axis=1)
@@ -182,8 +181,11 @@ def check_steplocked(gpu, cpu, steps, a, beta_t=1.0, tie_tol=TIE_TOL):
             mism_total += int((~same_pos).sum())
             agree_acc = same_pos & acc_cpu
             assert logpdf_close(glp[sl][agree_acc], cpu.lp[sl][agree_acc]).all(), "accepted log-density parity"
-            assert np.array_equal(glp[sl][same_pos & ~acc_cpu], before_lp[sl][same_pos & ~acc_cpu], equal_nan=True)
-            del moved_gpu
+            kept = same_pos & ~acc_cpu
+            if exact_lp:
+                assert np.array_equal(glp[sl][kept], before_lp[sl][kept], equal_nan=True)
+            else:
+                assert logpdf_close(glp[sl][kept], before_lp[sl][kept]).all()
         cpu.bare_counter += 1
     assert mism_total <= max(2, int(2e-4 * steps * 2 * H)), f"too many near-tie mismatches: {mism_total}"
 
@@ -227,7 +229,7 @@ def test_logistic_regression_small(factory):
     sf, gpu, cpu = make_pair(factory, model, 9, 1024, params, model.limits_array())
     st = gpu.get_state()
     assert logpdf_close(st["logfn"], cpu.lp, rtol=2e-5).all()
-    check_steplocked(gpu, cpu, steps=3, a=2.0, tie_tol=5e-3)
+    check_steplocked(gpu, cpu, steps=3, a=2.0, tie_tol=5e-3, exact_lp=False)
 
 
 def test_uniform_chain_bit_exact_over_many_steps(factory):
