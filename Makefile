@@ -6,7 +6,7 @@ LIB       := bayadera_b200/libbayadera_b200.so
 
 all: $(LIB) oracle
 
-$(LIB): $(CSRC)/engine.cu $(CSRC)/engine_estimate.inc $(CSRC)/kernels.cuh $(CSRC)/stretch_program.inc include/bayadera_b200.h
+$(LIB): $(wildcard $(CSRC)/*.cu $(CSRC)/*.cuh $(CSRC)/*.inc) include/bayadera_b200.h
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/engine.cu -ldl 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; exit 1)
 
 oracle:

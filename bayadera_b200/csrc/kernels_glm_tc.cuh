@@ -11,7 +11,7 @@
 //     every half-step.  Dropped term lo*lo and split residuals are ~2^-16 relative per product, zero-mean.
 //   * Persistent, warp-specialised CTA (1 per SM): warp 8 = TMA producer (3-stage ring of 32 KB X tiles),
 //     warp 9 = TMEM allocator + single-thread MMA issuer (4 accumulator stages of 128 columns),
-//     warps 0-3 / 4-7 = two epilogue groups draining alternate accumulator stages.
+//     warps 0-15 = four epilogue groups (4 warps = 128 TMEM lanes each), group g drains accumulator stage g.
 //   * softplus(e) = max(e,0) + log(1 + exp(-|e|)); the log is taken of a running PRODUCT of 64 factors (1+t),
 //     so the epilogue costs one MUFU.EX2 per element and one MUFU.LG2 per 64 (MUFU is the binding unit).
 // There is no counterpart in the reference (its LOGFN loops over the dataset serially in every thread,
@@ -31,7 +31,8 @@ constexpr int NSTAGE = 3;                       // X-tile ring
 constexpr int NACC = 4;                         // TMEM accumulator stages (4 x 128 columns = 512)
 constexpr int MAX_WB = 4;                       // walker blocks per launch (512 walkers)
 constexpr uint32_t TILE_BYTES = TILE * KD * 2;  // one bf16 plane of a tile: 16 KB
-constexpr int THREADS = 320;                    // 8 epilogue warps + TMA warp + MMA warp
+constexpr int NGRP = 4;                         // epilogue groups (4 warps each), one per accumulator stage
+constexpr int THREADS = (4 * NGRP + 2) * 32;    // 16 epilogue warps + TMA warp + MMA warp
 constexpr uint32_t IDESC =                      // kind::f16: D=f32, A=B=bf16, both K-major, N=128, M=128
     (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
 
@@ -110,8 +111,8 @@ __device__ __forceinline__ float lg2_approx(float x) {
 
 // ------------------------------------------------------------------ the kernel --
 // map_xh/map_xl: [rows][64] bf16 planes of the dataset; map_ah/map_al: [n_walkers][64] bf16 planes of the
-// walker block (hi, lo), origin at the first walker of this launch.  partial: [2*gridDim.x][ldp] doubles;
-// entry (2*cta + group, wb*128 + lane) = that epilogue thread's sum.
+// walker block (hi, lo), origin at the first walker of this launch.  partial: [NGRP*gridDim.x][ldp] doubles;
+// entry (NGRP*cta + group, wb*128 + lane) = that epilogue thread's sum.
 template <int NWB>
 __global__ void __launch_bounds__(THREADS, 1)
 k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
@@ -139,7 +140,7 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         mbar_init(a_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 9) {   // TMEM: all 512 columns (one CTA per SM)
+    if (warp == 4 * NGRP + 1) {   // TMEM: all 512 columns (one CTA per SM)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -148,7 +149,7 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 8) {
+    if (warp == 4 * NGRP) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             mbar_expect_tx(a_bar, NWB * 2 * TILE_BYTES);
@@ -165,7 +166,7 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                 tma_load_2d(b_base + (2 * s + 1) * TILE_BYTES, &map_xl, 0, row0, &full_bar[s]);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 4 * NGRP + 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             mbar_wait(a_bar, 0);
@@ -197,8 +198,9 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         }
     } else {
         // ===================== epilogue groups =====================
-        const uint32_t grp = warp >> 2;                  // 0: warps 0-3, 1: warps 4-7
+        const uint32_t grp = warp >> 2;                  // accumulator stage this group drains
         const uint32_t quarter = warp & 3;               // TMEM lanes 32*quarter .. +31
+        const uint32_t tbase = tmem_base + ((quarter * 32u) << 16) + grp * TILE;
         double acc64[NWB];
 #pragma unroll
         for (int wb = 0; wb < NWB; wb++) acc64[wb] = 0.0;
@@ -208,51 +210,61 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
             const uint32_t valid = min((uint32_t)TILE, rows - row0);
 #pragma unroll
             for (int wb = 0; wb < NWB; wb++, item++) {
-                if ((item & 1u) != grp) continue;
-                const uint32_t a = item % NACC, aph = (item / NACC) & 1u;
-                mbar_wait(&tfull_bar[a], aph);
+                if ((item % NACC) != grp) continue;
+                const uint32_t aph = (item / NACC) & 1u;
+                mbar_wait(&tfull_bar[grp], aph);
                 tc_fence_after();
-                float m = 0.f, lg = 0.f, p = 1.f;
+                // four independent (product, max-sum) chains; chunk c+1 is in flight while chunk c is reduced
+                float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, p0 = 1.f, p1 = 1.f, p2 = 1.f, p3 = 1.f;
+                uint32_t ra[32], rb[32];
+                auto reduce = [&](const uint32_t (&r)[32], const uint32_t col0) {
 #pragma unroll
-                for (int c = 0; c < TILE / 32; c++) {
-                    uint32_t r[32];
-                    BAY_TMEM_LD32(r, tmem_base + ((quarter * 32u) << 16) + a * TILE + c * 32);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (valid == TILE) {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const float e = __uint_as_float(r[j]);
-                            const float t = ex2_approx(-fabsf(e) * 1.4426950408889634f);
-                            p = fmaf(p, t, p);
-                            m += fmaxf(e, 0.f);
+                    for (int j = 0; j < 32; j += 4) {
+                        float e0 = __uint_as_float(r[j]), e1 = __uint_as_float(r[j + 1]);
+                        float e2 = __uint_as_float(r[j + 2]), e3 = __uint_as_float(r[j + 3]);
+                        if (valid != TILE) {             // last, partial tile: TMA zero-filled rows must not count
+                            e0 = (col0 + j < valid) ? e0 : -INFINITY;
+                            e1 = (col0 + j + 1 < valid) ? e1 : -INFINITY;
+                            e2 = (col0 + j + 2 < valid) ? e2 : -INFINITY;
+                            e3 = (col0 + j + 3 < valid) ? e3 : -INFINITY;
                         }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            if ((uint32_t)(c * 32 + j) < valid) {
-                                const float e = __uint_as_float(r[j]);
-                                const float t = ex2_approx(-fabsf(e) * 1.4426950408889634f);
-                                p = fmaf(p, t, p);
-                                m += fmaxf(e, 0.f);
-                            }
-                        }
+                        const float t0 = ex2_approx(-fabsf(e0) * 1.4426950408889634f);
+                        const float t1 = ex2_approx(-fabsf(e1) * 1.4426950408889634f);
+                        const float t2 = ex2_approx(-fabsf(e2) * 1.4426950408889634f);
+                        const float t3 = ex2_approx(-fabsf(e3) * 1.4426950408889634f);
+                        p0 = fmaf(p0, t0, p0); p1 = fmaf(p1, t1, p1); p2 = fmaf(p2, t2, p2); p3 = fmaf(p3, t3, p3);
+                        m0 += fmaxf(e0, 0.f); m1 += fmaxf(e1, 0.f); m2 += fmaxf(e2, 0.f); m3 += fmaxf(e3, 0.f);
                     }
-                    if (c & 1) { lg += lg2_approx(p); p = 1.f; }   // <= 2^64: no overflow
-                }
+                };
+                BAY_TMEM_LD32(ra, tbase);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                BAY_TMEM_LD32(rb, tbase + 32);
+                reduce(ra, 0);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                BAY_TMEM_LD32(ra, tbase + 64);
+                reduce(rb, 32);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                BAY_TMEM_LD32(rb, tbase + 96);
+                reduce(ra, 64);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // every column of the stage is in registers: hand the accumulator back before the last reduction
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[a]);
-                acc64[wb] += (double)fmaf(lg, 0.6931471805599453f, m);
+                if (lane == 0) mbar_arrive(&tempty_bar[grp]);
+                reduce(rb, 96);
+                // each chain holds 32 factors <= 2 (softplus(-inf) contributes exactly 0: t = 0, max = 0)
+                const float lg = lg2_approx(p0 * p1) + lg2_approx(p2 * p3);
+                acc64[wb] += (double)fmaf(lg, 0.6931471805599453f, (m0 + m1) + (m2 + m3));
             }
         }
-        const size_t base = (size_t)(2 * blockIdx.x + grp) * ldp + quarter * 32 + lane;
+        const size_t base = (size_t)(NGRP * blockIdx.x + grp) * ldp + quarter * 32 + lane;
 #pragma unroll
         for (int wb = 0; wb < NWB; wb++) partial[base + wb * TILE] = acc64[wb];
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == 4 * NGRP + 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
