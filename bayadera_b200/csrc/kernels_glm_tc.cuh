@@ -109,12 +109,20 @@ __device__ __forceinline__ float lg2_approx(float x) {
           "=r"(r[30]), "=r"(r[31])                                                                           \
         : "r"(taddr) : "memory")
 
+#define BAY_TMEM_LD16(r, taddr)                                                                              \
+    asm volatile(                                                                                            \
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                            \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                     \
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),      \
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])  \
+        : "r"(taddr) : "memory")
+
 // ------------------------------------------------------------------ the kernel --
 // map_xh/map_xl: [rows][64] bf16 planes of the dataset; map_ah/map_al: [n_walkers][64] bf16 planes of the
 // walker block (hi, lo), origin at the first walker of this launch.  partial: [NGRP*gridDim.x][ldp] doubles;
 // entry (NGRP*cta + group, wb*128 + lane) = that epilogue thread's sum.
 template <int NWB>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, 1)  // NWB in {1, 2, 4}
 k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                 const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                 const uint32_t rows, const uint32_t n_tiles, double* __restrict__ partial, const uint32_t ldp) {
@@ -198,68 +206,69 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         }
     } else {
         // ===================== epilogue groups =====================
-        const uint32_t grp = warp >> 2;                  // accumulator stage this group drains
+        // Group g drains accumulator stage g, i.e. items g, g+4, g+8, ... (item = tile*NWB + wb), which for
+        // NWB in {1,2,4} all belong to ONE walker block wb = g % NWB: a thread owns exactly one walker.
+        // The loops are kept rolled on purpose: fully unrolled, the epilogue was ~100 KB of SASS and the
+        // kernel stalled on instruction fetch (ncu: stall_no_inst).
+        const uint32_t grp = warp >> 2;
         const uint32_t quarter = warp & 3;               // TMEM lanes 32*quarter .. +31
+        const uint32_t wb_mine = grp % NWB;
         const uint32_t tbase = tmem_base + ((quarter * 32u) << 16) + grp * TILE;
-        double acc64[NWB];
-#pragma unroll
-        for (int wb = 0; wb < NWB; wb++) acc64[wb] = 0.0;
-        uint32_t item = 0;
-        for (uint32_t it = 0; it < my_tiles; it++) {
+        const uint32_t n_items = my_tiles * NWB;
+        double acc64 = 0.0;
+        for (uint32_t item = grp; item < n_items; item += NACC) {
+            const uint32_t it = item / NWB;
             const uint32_t row0 = (blockIdx.x + it * gridDim.x) * TILE;
             const uint32_t valid = min((uint32_t)TILE, rows - row0);
+            mbar_wait(&tfull_bar[grp], (item / NACC) & 1u);
+            tc_fence_after();
+            // four independent (product, max-sum) chains; the next 16 columns are in flight while 16 are reduced
+            float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, p0 = 1.f, p1 = 1.f, p2 = 1.f, p3 = 1.f;
+            uint32_t ra[16], rb[16];
+            auto reduce = [&](const uint32_t (&r)[16]) {
 #pragma unroll
-            for (int wb = 0; wb < NWB; wb++, item++) {
-                if ((item % NACC) != grp) continue;
-                const uint32_t aph = (item / NACC) & 1u;
-                mbar_wait(&tfull_bar[grp], aph);
-                tc_fence_after();
-                // four independent (product, max-sum) chains; chunk c+1 is in flight while chunk c is reduced
-                float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, p0 = 1.f, p1 = 1.f, p2 = 1.f, p3 = 1.f;
-                uint32_t ra[32], rb[32];
-                auto reduce = [&](const uint32_t (&r)[32], const uint32_t col0) {
+                for (int j = 0; j < 16; j += 4) {
+                    const float e0 = __uint_as_float(r[j]), e1 = __uint_as_float(r[j + 1]);
+                    const float e2 = __uint_as_float(r[j + 2]), e3 = __uint_as_float(r[j + 3]);
+                    const float t0 = ex2_approx(-fabsf(e0) * 1.4426950408889634f);
+                    const float t1 = ex2_approx(-fabsf(e1) * 1.4426950408889634f);
+                    const float t2 = ex2_approx(-fabsf(e2) * 1.4426950408889634f);
+                    const float t3 = ex2_approx(-fabsf(e3) * 1.4426950408889634f);
+                    p0 = fmaf(p0, t0, p0); p1 = fmaf(p1, t1, p1); p2 = fmaf(p2, t2, p2); p3 = fmaf(p3, t3, p3);
+                    m0 += fmaxf(e0, 0.f); m1 += fmaxf(e1, 0.f); m2 += fmaxf(e2, 0.f); m3 += fmaxf(e3, 0.f);
+                }
+            };
+            auto mask = [&](uint32_t (&r)[16], const uint32_t col0) {   // partial last tile: zero-filled rows -> -inf
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float e0 = __uint_as_float(r[j]), e1 = __uint_as_float(r[j + 1]);
-                        float e2 = __uint_as_float(r[j + 2]), e3 = __uint_as_float(r[j + 3]);
-                        if (valid != TILE) {             // last, partial tile: TMA zero-filled rows must not count
-                            e0 = (col0 + j < valid) ? e0 : -INFINITY;
-                            e1 = (col0 + j + 1 < valid) ? e1 : -INFINITY;
-                            e2 = (col0 + j + 2 < valid) ? e2 : -INFINITY;
-                            e3 = (col0 + j + 3 < valid) ? e3 : -INFINITY;
-                        }
-                        const float t0 = ex2_approx(-fabsf(e0) * 1.4426950408889634f);
-                        const float t1 = ex2_approx(-fabsf(e1) * 1.4426950408889634f);
-                        const float t2 = ex2_approx(-fabsf(e2) * 1.4426950408889634f);
-                        const float t3 = ex2_approx(-fabsf(e3) * 1.4426950408889634f);
-                        p0 = fmaf(p0, t0, p0); p1 = fmaf(p1, t1, p1); p2 = fmaf(p2, t2, p2); p3 = fmaf(p3, t3, p3);
-                        m0 += fmaxf(e0, 0.f); m1 += fmaxf(e1, 0.f); m2 += fmaxf(e2, 0.f); m3 += fmaxf(e3, 0.f);
-                    }
-                };
-                BAY_TMEM_LD32(ra, tbase);
+                for (int j = 0; j < 16; j++) r[j] = (col0 + j < valid) ? r[j] : 0xff800000u;
+            };
+            BAY_TMEM_LD16(ra, tbase);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll 1
+            for (uint32_t c = 0; c < TILE; c += 32) {
+                BAY_TMEM_LD16(rb, tbase + c + 16);
+                if (valid != TILE) mask(ra, c);
+                reduce(ra);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                BAY_TMEM_LD32(rb, tbase + 32);
-                reduce(ra, 0);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                BAY_TMEM_LD32(ra, tbase + 64);
-                reduce(rb, 32);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                BAY_TMEM_LD32(rb, tbase + 96);
-                reduce(ra, 64);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                // every column of the stage is in registers: hand the accumulator back before the last reduction
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[grp]);
-                reduce(rb, 96);
-                // each chain holds 32 factors <= 2 (softplus(-inf) contributes exactly 0: t = 0, max = 0)
-                const float lg = lg2_approx(p0 * p1) + lg2_approx(p2 * p3);
-                acc64[wb] += (double)fmaf(lg, 0.6931471805599453f, (m0 + m1) + (m2 + m3));
+                if (c + 32 < TILE) {
+                    BAY_TMEM_LD16(ra, tbase + c + 32);
+                } else {
+                    // every column of the stage is in registers: hand the accumulator back before the last reduction
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[grp]);
+                }
+                if (valid != TILE) mask(rb, c + 16);
+                reduce(rb);
+                if (c + 32 < TILE) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             }
+            // each chain holds 32 factors <= 2 (softplus(-inf) contributes exactly 0: t = 0, max = 0)
+            const float lg = lg2_approx(p0 * p1) + lg2_approx(p2 * p3);
+            acc64 += (double)fmaf(lg, 0.6931471805599453f, (m0 + m1) + (m2 + m3));
         }
         const size_t base = (size_t)(NGRP * blockIdx.x + grp) * ldp + quarter * 32 + lane;
 #pragma unroll
-        for (int wb = 0; wb < NWB; wb++) partial[base + wb * TILE] = acc64[wb];
+        for (int wb = 0; wb < NWB; wb++) partial[base + wb * TILE] = (wb == (int)wb_mine) ? acc64 : 0.0;
     }
 
     tc_fence_before();
