@@ -275,6 +275,7 @@ struct bay_sampler {
     uint64_t glm_rows = 0;                    // local rows (this rank's shard)
     float* glm_x = nullptr;                   // rows x D row-major
     double* glm_sy = nullptr;                 // D: X^T y (all-reduced over row shards)
+    double* glm_sx = nullptr;                 // D: column sums of the LOCAL rows
     float* glm_yt = nullptr;                  // D x W proposals / points, SoA
     float* glm_z = nullptr;                   // H
     float* glm_u = nullptr;                   // H

@@ -443,17 +443,21 @@ __global__ void k_glm_repack(const float* __restrict__ data, uint64_t rows, uint
 
 // sy[i] += sum_r y_r * x_{r,i}; one CTA per row chunk, thread = dimension (dim <= blockDim.x),
 // double accumulation, one atomicAdd(double) per (chunk, dim).
+// sx[i] += sum_r x_{r,i} (column sums; used by the tensor-core path, may be NULL).
 __global__ void k_glm_xty(const float* __restrict__ data, uint64_t rows, uint32_t dim,
-                          uint64_t rows_per_block, double* __restrict__ sy) {
+                          uint64_t rows_per_block, double* __restrict__ sy, double* __restrict__ sx) {
     const uint64_t r0 = (uint64_t)blockIdx.x * rows_per_block;
     const uint64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
     for (uint32_t i = threadIdx.x; i < dim; i += blockDim.x) {
-        double s = 0.0;
+        double s = 0.0, c = 0.0;
         for (uint64_t r = r0; r < r1; r++) {
             const float* row = data + r * (dim + 1);
-            s += (double)row[0] * (double)row[1 + i];
+            const double x = (double)row[1 + i];
+            s += (double)row[0] * x;
+            c += x;
         }
         atomicAdd(&sy[i], s);
+        if (sx) atomicAdd(&sx[i], c);
     }
 }
 

@@ -215,39 +215,37 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         const uint32_t wb_mine = grp % NWB;
         const uint32_t tbase = tmem_base + ((quarter * 32u) << 16) + grp * TILE;
         const uint32_t n_items = my_tiles * NWB;
-        double acc64 = 0.0;
+        // The walker block arrives pre-scaled by log2(e), so the accumulators hold a = eta*log2(e) and
+        //   softplus(eta) = max(eta,0) + ln2*log2(1 + 2^-|a|),   sum_rows max(eta,0) = (sum eta + sum |eta|)/2,
+        // where sum_rows eta = (sum_rows x_row) . theta is added analytically by k_glm_finish_tc.  Per element that
+        // leaves MUFU.EX2(-|a|), one FFMA on the running product and one FADD on sum|a|.
+        // Rows that TMA zero-filled past the end of the dataset give a = 0 exactly: no |a|, factor 2 -> corrected
+        // by subtracting (TILE - valid) from the log2 sum.
+        float hi = 0.f, lo = 0.f;                        // two-float (compensated) sum over this thread's items
         for (uint32_t item = grp; item < n_items; item += NACC) {
             const uint32_t it = item / NWB;
             const uint32_t row0 = (blockIdx.x + it * gridDim.x) * TILE;
             const uint32_t valid = min((uint32_t)TILE, rows - row0);
             mbar_wait(&tfull_bar[grp], (item / NACC) & 1u);
             tc_fence_after();
-            // four independent (product, max-sum) chains; the next 16 columns are in flight while 16 are reduced
+            // four independent (product, |a|-sum) chains; the next 16 columns are in flight while 16 are reduced
             float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, p0 = 1.f, p1 = 1.f, p2 = 1.f, p3 = 1.f;
             uint32_t ra[16], rb[16];
             auto reduce = [&](const uint32_t (&r)[16]) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
-                    const float e0 = __uint_as_float(r[j]), e1 = __uint_as_float(r[j + 1]);
-                    const float e2 = __uint_as_float(r[j + 2]), e3 = __uint_as_float(r[j + 3]);
-                    const float t0 = ex2_approx(-fabsf(e0) * 1.4426950408889634f);
-                    const float t1 = ex2_approx(-fabsf(e1) * 1.4426950408889634f);
-                    const float t2 = ex2_approx(-fabsf(e2) * 1.4426950408889634f);
-                    const float t3 = ex2_approx(-fabsf(e3) * 1.4426950408889634f);
+                    const float e0 = fabsf(__uint_as_float(r[j])), e1 = fabsf(__uint_as_float(r[j + 1]));
+                    const float e2 = fabsf(__uint_as_float(r[j + 2])), e3 = fabsf(__uint_as_float(r[j + 3]));
+                    const float t0 = ex2_approx(-e0), t1 = ex2_approx(-e1), t2 = ex2_approx(-e2), t3 = ex2_approx(-e3);
                     p0 = fmaf(p0, t0, p0); p1 = fmaf(p1, t1, p1); p2 = fmaf(p2, t2, p2); p3 = fmaf(p3, t3, p3);
-                    m0 += fmaxf(e0, 0.f); m1 += fmaxf(e1, 0.f); m2 += fmaxf(e2, 0.f); m3 += fmaxf(e3, 0.f);
+                    m0 += e0; m1 += e1; m2 += e2; m3 += e3;
                 }
-            };
-            auto mask = [&](uint32_t (&r)[16], const uint32_t col0) {   // partial last tile: zero-filled rows -> -inf
-#pragma unroll
-                for (int j = 0; j < 16; j++) r[j] = (col0 + j < valid) ? r[j] : 0xff800000u;
             };
             BAY_TMEM_LD16(ra, tbase);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll 1
             for (uint32_t c = 0; c < TILE; c += 32) {
                 BAY_TMEM_LD16(rb, tbase + c + 16);
-                if (valid != TILE) mask(ra, c);
                 reduce(ra);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (c + 32 < TILE) {
@@ -258,14 +256,18 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty_bar[grp]);
                 }
-                if (valid != TILE) mask(rb, c + 16);
                 reduce(rb);
                 if (c + 32 < TILE) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             }
-            // each chain holds 32 factors <= 2 (softplus(-inf) contributes exactly 0: t = 0, max = 0)
-            const float lg = lg2_approx(p0 * p1) + lg2_approx(p2 * p3);
-            acc64 += (double)fmaf(lg, 0.6931471805599453f, (m0 + m1) + (m2 + m3));
+            // each chain holds 32 factors <= 2.  item value (in units of ln2): sum log2(1+t) + sum|a|/2
+            const float lg = (lg2_approx(p0 * p1) + lg2_approx(p2 * p3)) - (float)(TILE - valid);
+            const float x = fmaf(0.5f, (m0 + m1) + (m2 + m3), lg);
+            const float s = hi + x;                      // Knuth two-sum: (hi, lo) += x without fp64 (DADD is slow here)
+            const float bp = s - hi;
+            lo += (hi - (s - bp)) + (x - bp);
+            hi = s;
         }
+        const double acc64 = ((double)hi + (double)lo) * 0.6931471805599453;
         const size_t base = (size_t)(NGRP * blockIdx.x + grp) * ldp + quarter * 32 + lane;
 #pragma unroll
         for (int wb = 0; wb < NWB; wb++) partial[base + wb * TILE] = (wb == (int)wb_mine) ? acc64 : 0.0;
@@ -279,16 +281,32 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     }
 }
 
-// points (SoA, dim 64 x n, pitch) -> bf16 hi/lo planes [n][64] (row = walker), for the A operand
+constexpr float LOG2E = 1.4426950408889634f;
+
+// points (SoA, dim 64 x n, pitch) -> bf16 hi/lo planes [n][64] (row = walker) of theta * log2(e), the A operand
 __global__ void k_glm_split_points(const float* __restrict__ pts, uint32_t pitch, uint32_t n,
                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;    // e = k*64 + i, coalesced stores
     if (e >= n * KD) return;
     const uint32_t k = e / KD, i = e % KD;
-    const float x = pts[(size_t)i * pitch + k];
+    const float x = __fmul_rn(pts[(size_t)i * pitch + k], LOG2E);
     const __nv_bfloat16 h = __float2bfloat16_rn(x);
     hi[e] = h;
     lo[e] = __float2bfloat16_rn(x - __bfloat162float(h));
+}
+
+// sp[k] = sum over the kernel's partial rows (fixed order) + (ln2/2) * sx . (theta_k * log2 e): the analytic
+// sum_rows eta term of  sum max(eta,0) = (sum eta + sum |eta|) / 2.  sx = column sums of the LOCAL rows.
+__global__ void k_glm_finish_tc(uint32_t n, uint32_t chunks, uint32_t ldp, const double* __restrict__ partial,
+                                const double* __restrict__ sx, const float* __restrict__ pts, uint32_t pitch,
+                                double* __restrict__ sp) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double s = 0.0;
+    for (uint32_t c = 0; c < chunks; c++) s += partial[(size_t)c * ldp + k];
+    double dot = 0.0;
+    for (uint32_t i = 0; i < KD; i++) dot += sx[i] * (double)__fmul_rn(pts[(size_t)i * pitch + k], LOG2E);
+    sp[k] = s + 0.5 * 0.6931471805599453 * dot;
 }
 
 // dataset rows [y, x_1..x_64] (stride 65) -> bf16 hi/lo planes [rows][64]
