@@ -2,19 +2,22 @@
 //
 // Computes, for up to 512 walkers per launch and ALL local dataset rows,
 //     sp[w] = sum_rows softplus( x_row . theta_w )
-// as the dense contraction  S(128 walkers x 128 rows) = Theta_blk(128 x 64) . X_tile(128 x 64)^T  on the
+// as the dense contraction  S(128 walkers x 64 rows) = Theta_blk(128 x 64) . X_halftile(64 x 64)^T  on the
 // 5th-generation tensor cores, followed by a thread-local softplus reduction:
 //   * TMEM lanes = walkers, TMEM columns = dataset rows, so every epilogue thread owns one walker and sums
 //     over the columns it reads with tcgen05.ld — no cross-lane reduction at all.
 //   * fp32-level accuracy from bf16 inputs by a 3-term split (hi*hi + hi*lo + lo*hi), fp32 accumulation in TMEM:
 //     the dataset is split ONCE into (Xh, Xl) bf16 planes (same HBM bytes as the fp32 matrix), the walker block
 //     every half-step.  Dropped term lo*lo and split residuals are ~2^-16 relative per product, zero-mean.
-//   * Persistent, warp-specialised CTA (1 per SM): warp 8 = TMA producer (3-stage ring of 32 KB X tiles),
-//     warp 9 = TMEM allocator + single-thread MMA issuer (4 accumulator stages of 128 columns),
-//     warps 0-15 = four epilogue groups (4 warps = 128 TMEM lanes each), group g drains accumulator stage g.
-//   * softplus(e) = max(e,0) + log(1 + exp(-|e|)); the log is taken of a running PRODUCT of 64 factors (1+t),
-//     so the epilogue costs one exp2 per element and one MUFU.LG2 per 64; MUFU.EX2 bounds it, so every fourth
-//     exp2 is evaluated by an FMA-pipe polynomial instead.
+//   * Persistent, warp-specialised CTA (1 per SM): warp 16 = TMA producer (3-stage ring of 32 KB X tiles),
+//     warp 17 = TMEM allocator + single-thread MMA issuer, warps 0-15 = four epilogue groups (4 warps = 128 TMEM
+//     lanes each).  TMEM holds EIGHT accumulator stages of 64 columns; group g owns stages g and g+4, so the
+//     MMA that refills one of them overlaps the drain of the other (with one stage per group the period was
+//     MMA + drain: ncu showed tensor 63 % / MUFU 84 % busy, neither saturated).
+//   * The walker block arrives pre-scaled by log2(e): accumulators hold a = eta*log2(e) and
+//       softplus(eta) = max(eta,0) + ln2*log2(1 + 2^-|a|),   sum_rows max(eta,0) = (sum eta + sum |eta|)/2,
+//     with sum_rows eta = (sum_rows x_row) . theta added analytically (k_glm_finish_tc).  The log is taken of a
+//     running PRODUCT of 16 factors (1+t) per chain, so an element costs MUFU.EX2(-|a|) + one FFMA + one FADD.
 // There is no counterpart in the reference (its LOGFN loops over the dataset serially in every thread,
 // e.g. K/cuda/distributions/gaussian.cu:40-42); the arithmetic contract is the oracle's serial model.
 #pragma once
@@ -26,16 +29,18 @@
 namespace bay {
 namespace tc {
 
-constexpr int TILE = 128;                       // MMA M (walkers per block) and N (rows per tile)
+constexpr int TILE = 128;                       // MMA M (walkers per block); rows per TMA tile
+constexpr int CN = 64;                          // MMA N: dataset rows per accumulator stage (half a tile)
 constexpr int KD = 64;                          // model dimension handled by this kernel
 constexpr int NSTAGE = 3;                       // X-tile ring
-constexpr int NACC = 4;                         // TMEM accumulator stages (4 x 128 columns = 512)
+constexpr int NACC = 8;                         // TMEM accumulator stages (8 x 64 columns = 512)
 constexpr int MAX_WB = 4;                       // walker blocks per launch (512 walkers)
 constexpr uint32_t TILE_BYTES = TILE * KD * 2;  // one bf16 plane of a tile: 16 KB
-constexpr int NGRP = 4;                         // epilogue groups (4 warps each), one per accumulator stage
+constexpr int NGRP = 4;                         // epilogue groups (4 warps each); group g drains stages g, g+4
 constexpr int THREADS = (4 * NGRP + 2) * 32;    // 16 epilogue warps + TMA warp + MMA warp
-constexpr uint32_t IDESC =                      // kind::f16: D=f32, A=B=bf16, both K-major, N=128, M=128
-    (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+constexpr uint32_t IDESC =                      // kind::f16: D=f32, A=B=bf16, both K-major, N=64, M=128
+    (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CN >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+constexpr float LOG2E = 1.4426950408889634f;
 
 __host__ __device__ constexpr size_t smem_bytes(int nwb) {
     return 1024 /*alignment slack*/ + (size_t)nwb * 2 * TILE_BYTES + (size_t)NSTAGE * 2 * TILE_BYTES + 256;
@@ -94,7 +99,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 // 2^x for x <= 0 on the FMA/ALU pipes (no MUFU): Cody-Waite split x = n + f, |f| <= 1/2, degree-5 minimax of 2^f
 // (max relative error 2.3e-7 in fp32 Horner form, i.e. the accuracy of MUFU.EX2), exponent patched in by integer add.
-// Used for one element in four so that the MUFU pipe, which otherwise bounds the epilogue, sheds 25 % of its load.
 __device__ __forceinline__ float ex2_poly(float x) {
     const float xc = fmaxf(x, -126.0f);
     const float r = xc + 12582912.0f;                 // 1.5 * 2^23: n = round(xc) lands in the low mantissa bits
@@ -113,18 +117,6 @@ __device__ __forceinline__ float lg2_approx(float x) {
     return y;
 }
 
-#define BAY_TMEM_LD32(r, taddr)                                                                              \
-    asm volatile(                                                                                            \
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                            \
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                            \
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"            \
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),      \
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), \
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),          \
-          "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),          \
-          "=r"(r[30]), "=r"(r[31])                                                                           \
-        : "r"(taddr) : "memory")
-
 #define BAY_TMEM_LD16(r, taddr)                                                                              \
     asm volatile(                                                                                            \
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                            \
@@ -132,16 +124,21 @@ __device__ __forceinline__ float lg2_approx(float x) {
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),      \
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])  \
         : "r"(taddr) : "memory")
+#define BAY_TMEM_WAIT_LD() asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
 
 // ------------------------------------------------------------------ the kernel --
 // map_xh/map_xl: [rows][64] bf16 planes of the dataset; map_ah/map_al: [n_walkers][64] bf16 planes of the
-// walker block (hi, lo), origin at the first walker of this launch.  partial: [NGRP*gridDim.x][ldp] doubles;
-// entry (NGRP*cta + group, wb*128 + lane) = that epilogue thread's sum.
-template <int NWB>
-__global__ void __launch_bounds__(THREADS, 1)  // NWB in {1, 2, 4}
+// walker block (hi, lo; already scaled by log2 e), origin at the first walker of this launch.
+// Work item = (tile, half, walker block): item = (tile*2 + half)*NWB + wb, accumulator stage = item % 8,
+// epilogue group = item % 4 — for NWB in {1,2,4} a group always sees the same walker block wb = group % NWB.
+// partial: [NGRP*gridDim.x][ldp] doubles; entry (NGRP*cta + group, wb*128 + lane) = that epilogue thread's sum.
+// POLY: every fourth exp2 is evaluated by ex2_poly on the FMA pipe instead of MUFU.
+template <int NWB, bool POLY>
+__global__ void __launch_bounds__(THREADS, 1)
 k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                 const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                 const uint32_t rows, const uint32_t n_tiles, double* __restrict__ partial, const uint32_t ldp) {
+    static_assert(NWB == 1 || NWB == 2 || NWB == 4, "walker blocks per launch");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* a_hi = smem;                                   // NWB tiles
@@ -199,50 +196,47 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                 const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-                const uint64_t bh = make_desc(smem_u32(b_base + (2 * s) * TILE_BYTES));
-                const uint64_t bl = make_desc(smem_u32(b_base + (2 * s + 1) * TILE_BYTES));
+#pragma unroll 1
+                for (int half = 0; half < 2; half++) {
+                    // rows 64*half .. +63 of the tile: 8 swizzle atoms (8 rows x 128 B) further on
+                    const uint64_t bh = make_desc(smem_u32(b_base + (2 * s) * TILE_BYTES + half * (CN * KD * 2)));
+                    const uint64_t bl = make_desc(smem_u32(b_base + (2 * s + 1) * TILE_BYTES + half * (CN * KD * 2)));
 #pragma unroll
-                for (int wb = 0; wb < NWB; wb++, item++) {
-                    const uint32_t a = item % NACC, aph = (item / NACC) & 1u;
-                    mbar_wait(&tempty_bar[a], aph ^ 1u);
-                    tc_fence_after();
-                    const uint32_t d = tmem_base + a * TILE;
-                    const uint64_t ah = make_desc(smem_u32(a_hi + wb * TILE_BYTES));
-                    const uint64_t al = make_desc(smem_u32(a_lo + wb * TILE_BYTES));
+                    for (int wb = 0; wb < NWB; wb++, item++) {
+                        const uint32_t a = item % NACC, aph = (item / NACC) & 1u;
+                        mbar_wait(&tempty_bar[a], aph ^ 1u);
+                        tc_fence_after();
+                        const uint32_t d = tmem_base + a * CN;
+                        const uint64_t ah = make_desc(smem_u32(a_hi + wb * TILE_BYTES));
+                        const uint64_t al = make_desc(smem_u32(a_lo + wb * TILE_BYTES));
 #pragma unroll
-                    for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, ah + 2 * k, bh + 2 * k, k > 0);   // hi*hi
+                        for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, ah + 2 * k, bh + 2 * k, k > 0);   // hi*hi
 #pragma unroll
-                    for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, ah + 2 * k, bl + 2 * k, 1);       // hi*lo
+                        for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, ah + 2 * k, bl + 2 * k, 1);       // hi*lo
 #pragma unroll
-                    for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, al + 2 * k, bh + 2 * k, 1);       // lo*hi
-                    tc_commit(&tfull_bar[a]);
+                        for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, al + 2 * k, bh + 2 * k, 1);       // lo*hi
+                        tc_commit(&tfull_bar[a]);
+                    }
                 }
                 tc_commit(&empty_bar[s]);   // the X tile is free once all MMAs that read it completed
             }
         }
     } else {
         // ===================== epilogue groups =====================
-        // Group g drains accumulator stage g, i.e. items g, g+4, g+8, ... (item = tile*NWB + wb), which for
-        // NWB in {1,2,4} all belong to ONE walker block wb = g % NWB: a thread owns exactly one walker.
         // The loops are kept rolled on purpose: fully unrolled, the epilogue was ~100 KB of SASS and the
         // kernel stalled on instruction fetch (ncu: stall_no_inst).
         const uint32_t grp = warp >> 2;
         const uint32_t quarter = warp & 3;               // TMEM lanes 32*quarter .. +31
         const uint32_t wb_mine = grp % NWB;
-        const uint32_t tbase = tmem_base + ((quarter * 32u) << 16) + grp * TILE;
-        const uint32_t n_items = my_tiles * NWB;
-        // The walker block arrives pre-scaled by log2(e), so the accumulators hold a = eta*log2(e) and
-        //   softplus(eta) = max(eta,0) + ln2*log2(1 + 2^-|a|),   sum_rows max(eta,0) = (sum eta + sum |eta|)/2,
-        // where sum_rows eta = (sum_rows x_row) . theta is added analytically by k_glm_finish_tc.  Per element that
-        // leaves MUFU.EX2(-|a|), one FFMA on the running product and one FADD on sum|a|.
-        // Rows that TMA zero-filled past the end of the dataset give a = 0 exactly: no |a|, factor 2 -> corrected
-        // by subtracting (TILE - valid) from the log2 sum.
+        const uint32_t n_items = my_tiles * 2 * NWB;
         float hi = 0.f, lo = 0.f;                        // two-float (compensated) sum over this thread's items
-        for (uint32_t item = grp; item < n_items; item += NACC) {
-            const uint32_t it = item / NWB;
-            const uint32_t row0 = (blockIdx.x + it * gridDim.x) * TILE;
-            const uint32_t valid = min((uint32_t)TILE, rows - row0);
-            mbar_wait(&tfull_bar[grp], (item / NACC) & 1u);
+        for (uint32_t item = grp; item < n_items; item += NGRP) {
+            const uint32_t a = item % NACC;
+            const uint32_t half_idx = item / NWB;        // = tile*2 + half
+            const uint32_t row0 = (blockIdx.x + (half_idx >> 1) * gridDim.x) * TILE + (half_idx & 1u) * CN;
+            const uint32_t valid = rows > row0 ? min((uint32_t)CN, rows - row0) : 0u;
+            const uint32_t tbase = tmem_base + ((quarter * 32u) << 16) + a * CN;
+            mbar_wait(&tfull_bar[a], (item / NACC) & 1u);
             tc_fence_after();
             // four independent (product, |a|-sum) chains; the next 16 columns are in flight while 16 are reduced
             float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, p0 = 1.f, p1 = 1.f, p2 = 1.f, p3 = 1.f;
@@ -252,31 +246,31 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                 for (int j = 0; j < 16; j += 4) {
                     const float e0 = fabsf(__uint_as_float(r[j])), e1 = fabsf(__uint_as_float(r[j + 1]));
                     const float e2 = fabsf(__uint_as_float(r[j + 2])), e3 = fabsf(__uint_as_float(r[j + 3]));
-                    const float t0 = ex2_approx(-e0), t1 = ex2_approx(-e1), t2 = ex2_approx(-e2), t3 = ex2_poly(-e3);
+                    const float t0 = ex2_approx(-e0), t1 = ex2_approx(-e1), t2 = ex2_approx(-e2);
+                    const float t3 = POLY ? ex2_poly(-e3) : ex2_approx(-e3);
                     p0 = fmaf(p0, t0, p0); p1 = fmaf(p1, t1, p1); p2 = fmaf(p2, t2, p2); p3 = fmaf(p3, t3, p3);
                     m0 += e0; m1 += e1; m2 += e2; m3 += e3;
                 }
             };
             BAY_TMEM_LD16(ra, tbase);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll 1
-            for (uint32_t c = 0; c < TILE; c += 32) {
-                BAY_TMEM_LD16(rb, tbase + c + 16);
-                reduce(ra);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c + 32 < TILE) {
-                    BAY_TMEM_LD16(ra, tbase + c + 32);
-                } else {
-                    // every column of the stage is in registers: hand the accumulator back before the last reduction
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty_bar[grp]);
-                }
-                reduce(rb);
-                if (c + 32 < TILE) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            }
-            // each chain holds 32 factors <= 2.  item value (in units of ln2): sum log2(1+t) + sum|a|/2
-            const float lg = (lg2_approx(p0 * p1) + lg2_approx(p2 * p3)) - (float)(TILE - valid);
+            BAY_TMEM_WAIT_LD();
+            BAY_TMEM_LD16(rb, tbase + 16);
+            reduce(ra);
+            BAY_TMEM_WAIT_LD();
+            BAY_TMEM_LD16(ra, tbase + 32);
+            reduce(rb);
+            BAY_TMEM_WAIT_LD();
+            BAY_TMEM_LD16(rb, tbase + 48);
+            reduce(ra);
+            BAY_TMEM_WAIT_LD();
+            // every column of the stage is in registers: hand the accumulator back before the last reduction
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[a]);
+            reduce(rb);
+            // Rows that TMA zero-filled past the end of the dataset give a = 0 exactly: |a| = 0, factor 2 -> subtract
+            // one per such row from the log2 sum.  Item value (in units of ln2): sum log2(1+t) + sum|a|/2.
+            const float lg = (lg2_approx(p0 * p1) + lg2_approx(p2 * p3)) - (float)(CN - valid);
             const float x = fmaf(0.5f, (m0 + m1) + (m2 + m3), lg);
             const float s = hi + x;                      // Knuth two-sum: (hi, lo) += x without fp64 (DADD is slow here)
             const float bp = s - hi;
@@ -296,8 +290,6 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
-
-constexpr float LOG2E = 1.4426950408889634f;
 
 // points (SoA, dim 64 x n, pitch) -> bf16 hi/lo planes [n][64] (row = walker) of theta * log2(e), the A operand
 __global__ void k_glm_split_points(const float* __restrict__ pts, uint32_t pitch, uint32_t n,
