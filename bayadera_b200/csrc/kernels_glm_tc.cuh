@@ -2,7 +2,7 @@
 //
 // Computes, for up to 512 walkers per launch and ALL local dataset rows,
 //     sp[w] = sum_rows softplus( x_row . theta_w )
-// as the dense contraction  S(128 walkers x 64 rows) = Theta_blk(128 x 64) . X_halftile(64 x 64)^T  on the
+// as the dense contraction  S(128 walkers x 128 rows) = Theta_blk(128 x 64) . X_tile(128 x 64)^T  on the
 // 5th-generation tensor cores, followed by a thread-local softplus reduction:
 //   * TMEM lanes = walkers, TMEM columns = dataset rows, so every epilogue thread owns one walker and sums
 //     over the columns it reads with tcgen05.ld — no cross-lane reduction at all.
@@ -10,10 +10,11 @@
 //     the dataset is split ONCE into (Xh, Xl) bf16 planes (same HBM bytes as the fp32 matrix), the walker block
 //     every half-step.  Dropped term lo*lo and split residuals are ~2^-16 relative per product, zero-mean.
 //   * Persistent, warp-specialised CTA (1 per SM): warp 16 = TMA producer (3-stage ring of 32 KB X tiles),
-//     warp 17 = TMEM allocator + single-thread MMA issuer, warps 0-15 = four epilogue groups (4 warps = 128 TMEM
-//     lanes each).  TMEM holds EIGHT accumulator stages of 64 columns; group g owns stages g and g+4, so the
-//     MMA that refills one of them overlaps the drain of the other (with one stage per group the period was
-//     MMA + drain: ncu showed tensor 63 % / MUFU 84 % busy, neither saturated).
+//     warp 17 = TMEM allocator + single-thread MMA issuer, warps 0-15 = two epilogue groups of 8 warps (4 TMEM
+//     lane quarters x 2 column halves).  TMEM holds four accumulator stages of 128 columns; group g owns stages
+//     g and g+2, so the MMA that refills one of them overlaps the drain of the other (with one stage per group
+//     the period was MMA + drain: ncu showed tensor 63 % / MUFU 84 % busy, neither saturated; 8 stages of 64
+//     columns were worse still because an N=64 MMA reads 6 KB of shared memory in 32 clk, over the 128 B/clk port).
 //   * The walker block arrives pre-scaled by log2(e): accumulators hold a = eta*log2(e) and
 //       softplus(eta) = max(eta,0) + ln2*log2(1 + 2^-|a|),   sum_rows max(eta,0) = (sum eta + sum |eta|)/2,
 //     with sum_rows eta = (sum_rows x_row) . theta added analytically (k_glm_finish_tc).  The log is taken of a
@@ -30,15 +31,16 @@ namespace bay {
 namespace tc {
 
 constexpr int TILE = 128;                       // MMA M (walkers per block); rows per TMA tile
-constexpr int CN = 64;                          // MMA N: dataset rows per accumulator stage (half a tile)
+constexpr int CN = 128;                         // MMA N: dataset rows per accumulator stage (one tile)
 constexpr int KD = 64;                          // model dimension handled by this kernel
 constexpr int NSTAGE = 3;                       // X-tile ring
-constexpr int NACC = 8;                         // TMEM accumulator stages (8 x 64 columns = 512)
+constexpr int NACC = 4;                         // TMEM accumulator stages (4 x 128 columns = 512)
 constexpr int MAX_WB = 4;                       // walker blocks per launch (512 walkers)
 constexpr uint32_t TILE_BYTES = TILE * KD * 2;  // one bf16 plane of a tile: 16 KB
-constexpr int NGRP = 4;                         // epilogue groups (4 warps each); group g drains stages g, g+4
-constexpr int THREADS = (4 * NGRP + 2) * 32;    // 16 epilogue warps + TMA warp + MMA warp
-constexpr uint32_t IDESC =                      // kind::f16: D=f32, A=B=bf16, both K-major, N=64, M=128
+constexpr int NGRP = 2;                         // epilogue groups (8 warps each); group g drains stages g, g+2
+constexpr int EPI_WARPS = 8 * NGRP;             // a group = 4 lane quarters x 2 column halves
+constexpr int THREADS = (EPI_WARPS + 2) * 32;   // 16 epilogue warps + TMA warp + MMA warp
+constexpr uint32_t IDESC =                      // kind::f16: D=f32, A=B=bf16, both K-major, N=128, M=128
     (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CN >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -129,9 +131,8 @@ __device__ __forceinline__ float lg2_approx(float x) {
 // ------------------------------------------------------------------ the kernel --
 // map_xh/map_xl: [rows][64] bf16 planes of the dataset; map_ah/map_al: [n_walkers][64] bf16 planes of the
 // walker block (hi, lo; already scaled by log2 e), origin at the first walker of this launch.
-// Work item = (tile, half, walker block): item = (tile*2 + half)*NWB + wb, accumulator stage = item % 8,
-// epilogue group = item % 4 — for NWB in {1,2,4} a group always sees the same walker block wb = group % NWB.
-// partial: [NGRP*gridDim.x][ldp] doubles; entry (NGRP*cta + group, wb*128 + lane) = that epilogue thread's sum.
+// Work item = (tile, walker block): item = tile*NWB + wb, accumulator stage = item % 4, epilogue group = item % 2.
+// partial: [2*NGRP*gridDim.x][ldp] doubles; row ((NGRP*cta + group)*2 + column half), entry wb*128 + lane.
 // POLY: every fourth exp2 is evaluated by ex2_poly on the FMA pipe instead of MUFU.
 template <int NWB, bool POLY>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -157,11 +158,11 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < NACC; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        for (int i = 0; i < NACC; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
         mbar_init(a_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4 * NGRP + 1) {   // TMEM: all 512 columns (one CTA per SM)
+    if (warp == EPI_WARPS + 1) {   // TMEM: all 512 columns (one CTA per SM)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -170,7 +171,7 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4 * NGRP) {
+    if (warp == EPI_WARPS) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             mbar_expect_tx(a_bar, NWB * 2 * TILE_BYTES);
@@ -187,7 +188,7 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                 tma_load_2d(b_base + (2 * s + 1) * TILE_BYTES, &map_xl, 0, row0, &full_bar[s]);
             }
         }
-    } else if (warp == 4 * NGRP + 1) {
+    } else if (warp == EPI_WARPS + 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             mbar_wait(a_bar, 0);
@@ -196,27 +197,23 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                 const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-#pragma unroll 1
-                for (int half = 0; half < 2; half++) {
-                    // rows 64*half .. +63 of the tile: 8 swizzle atoms (8 rows x 128 B) further on
-                    const uint64_t bh = make_desc(smem_u32(b_base + (2 * s) * TILE_BYTES + half * (CN * KD * 2)));
-                    const uint64_t bl = make_desc(smem_u32(b_base + (2 * s + 1) * TILE_BYTES + half * (CN * KD * 2)));
+                const uint64_t bh = make_desc(smem_u32(b_base + (2 * s) * TILE_BYTES));
+                const uint64_t bl = make_desc(smem_u32(b_base + (2 * s + 1) * TILE_BYTES));
 #pragma unroll
-                    for (int wb = 0; wb < NWB; wb++, item++) {
-                        const uint32_t a = item % NACC, aph = (item / NACC) & 1u;
-                        mbar_wait(&tempty_bar[a], aph ^ 1u);
-                        tc_fence_after();
-                        const uint32_t d = tmem_base + a * CN;
-                        const uint64_t ah = make_desc(smem_u32(a_hi + wb * TILE_BYTES));
-                        const uint64_t al = make_desc(smem_u32(a_lo + wb * TILE_BYTES));
+                for (int wb = 0; wb < NWB; wb++, item++) {
+                    const uint32_t a = item % NACC, aph = (item / NACC) & 1u;
+                    mbar_wait(&tempty_bar[a], aph ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + a * CN;
+                    const uint64_t ah = make_desc(smem_u32(a_hi + wb * TILE_BYTES));
+                    const uint64_t al = make_desc(smem_u32(a_lo + wb * TILE_BYTES));
 #pragma unroll
-                        for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, ah + 2 * k, bh + 2 * k, k > 0);   // hi*hi
+                    for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, ah + 2 * k, bh + 2 * k, k > 0);   // hi*hi
 #pragma unroll
-                        for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, ah + 2 * k, bl + 2 * k, 1);       // hi*lo
+                    for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, ah + 2 * k, bl + 2 * k, 1);       // hi*lo
 #pragma unroll
-                        for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, al + 2 * k, bh + 2 * k, 1);       // lo*hi
-                        tc_commit(&tfull_bar[a]);
-                    }
+                    for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, al + 2 * k, bh + 2 * k, 1);       // lo*hi
+                    tc_commit(&tfull_bar[a]);
                 }
                 tc_commit(&empty_bar[s]);   // the X tile is free once all MMAs that read it completed
             }
@@ -225,17 +222,19 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         // ===================== epilogue groups =====================
         // The loops are kept rolled on purpose: fully unrolled, the epilogue was ~100 KB of SASS and the
         // kernel stalled on instruction fetch (ncu: stall_no_inst).
-        const uint32_t grp = warp >> 2;
+        const uint32_t grp = warp >> 3;                  // 8 warps per group
         const uint32_t quarter = warp & 3;               // TMEM lanes 32*quarter .. +31
-        const uint32_t wb_mine = grp % NWB;
-        const uint32_t n_items = my_tiles * 2 * NWB;
-        float hi = 0.f, lo = 0.f;                        // two-float (compensated) sum over this thread's items
+        const uint32_t chalf = (warp >> 2) & 1u;         // columns 64*chalf .. +63 of the stage
+        const uint32_t n_items = my_tiles * NWB;
+        // Items of this group: item = grp, grp+2, ...; walker block wb = item % NWB.  For NWB = 4 a group
+        // alternates between two walker blocks (grp and grp+2): two accumulator pairs, selected by `sel`.
+        float hi0 = 0.f, lo0 = 0.f, hi1 = 0.f, lo1 = 0.f;   // two-float (compensated) sums
         for (uint32_t item = grp; item < n_items; item += NGRP) {
             const uint32_t a = item % NACC;
-            const uint32_t half_idx = item / NWB;        // = tile*2 + half
-            const uint32_t row0 = (blockIdx.x + (half_idx >> 1) * gridDim.x) * TILE + (half_idx & 1u) * CN;
-            const uint32_t valid = rows > row0 ? min((uint32_t)CN, rows - row0) : 0u;
-            const uint32_t tbase = tmem_base + ((quarter * 32u) << 16) + a * CN;
+            const uint32_t it = item / NWB;
+            const uint32_t row0 = (blockIdx.x + it * gridDim.x) * TILE + chalf * 64u;
+            const uint32_t valid = rows > row0 ? min(64u, rows - row0) : 0u;
+            const uint32_t tbase = tmem_base + ((quarter * 32u) << 16) + a * CN + chalf * 64u;
             mbar_wait(&tfull_bar[a], (item / NACC) & 1u);
             tc_fence_after();
             // four independent (product, |a|-sum) chains; the next 16 columns are in flight while 16 are reduced
@@ -263,29 +262,39 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
             BAY_TMEM_LD16(rb, tbase + 48);
             reduce(ra);
             BAY_TMEM_WAIT_LD();
-            // every column of the stage is in registers: hand the accumulator back before the last reduction
+            // every column of this warp's share is in registers: hand the accumulator back before the last reduction
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[a]);
             reduce(rb);
             // Rows that TMA zero-filled past the end of the dataset give a = 0 exactly: |a| = 0, factor 2 -> subtract
             // one per such row from the log2 sum.  Item value (in units of ln2): sum log2(1+t) + sum|a|/2.
-            const float lg = (lg2_approx(p0 * p1) + lg2_approx(p2 * p3)) - (float)(CN - valid);
+            const float lg = (lg2_approx(p0 * p1) + lg2_approx(p2 * p3)) - (float)(64u - valid);
             const float x = fmaf(0.5f, (m0 + m1) + (m2 + m3), lg);
+            const bool sel = (NWB == 4) && (((item / NGRP) & 1u) != 0u);
+            float& hi = sel ? hi1 : hi0;
+            float& lo = sel ? lo1 : lo0;
             const float s = hi + x;                      // Knuth two-sum: (hi, lo) += x without fp64 (DADD is slow here)
             const float bp = s - hi;
             lo += (hi - (s - bp)) + (x - bp);
             hi = s;
         }
-        const double acc64 = ((double)hi + (double)lo) * 0.6931471805599453;
-        const size_t base = (size_t)(NGRP * blockIdx.x + grp) * ldp + quarter * 32 + lane;
+        const double v0 = ((double)hi0 + (double)lo0) * 0.6931471805599453;
+        const double v1 = ((double)hi1 + (double)lo1) * 0.6931471805599453;
+        // partial row (cta, group, column half); walker blocks this thread never saw get 0
+        const size_t base = (size_t)((NGRP * blockIdx.x + grp) * 2 + chalf) * ldp + quarter * 32 + lane;
 #pragma unroll
-        for (int wb = 0; wb < NWB; wb++) partial[base + wb * TILE] = (wb == (int)wb_mine) ? acc64 : 0.0;
+        for (int wb = 0; wb < NWB; wb++) {
+            double v = 0.0;
+            if (NWB == 4) v = (wb == (int)grp) ? v0 : ((wb == (int)grp + 2) ? v1 : 0.0);
+            else v = (wb == (int)(grp % NWB)) ? v0 : 0.0;
+            partial[base + wb * TILE] = v;
+        }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4 * NGRP + 1) {
+    if (warp == EPI_WARPS + 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
