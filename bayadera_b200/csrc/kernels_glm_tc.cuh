@@ -9,16 +9,11 @@
 //   * fp32-level accuracy from bf16 inputs by a 3-term split (hi*hi + hi*lo + lo*hi), fp32 accumulation in TMEM:
 //     the dataset is split ONCE into (Xh, Xl) bf16 planes (same HBM bytes as the fp32 matrix), the walker block
 //     every half-step.  Dropped term lo*lo and split residuals are ~2^-16 relative per product, zero-mean.
-//   * Persistent, warp-specialised CTA (1 per SM): warp 16 = TMA producer (3-stage ring of 32 KB X tiles),
-//     warp 17 = TMEM allocator + single-thread MMA issuer, warps 0-15 = two epilogue groups of 8 warps (4 TMEM
-//     lane quarters x 2 column halves).  TMEM holds four accumulator stages of 128 columns; group g owns stages
-//     g and g+2, so the MMA that refills one of them overlaps the drain of the other (with one stage per group
-//     the period was MMA + drain: ncu showed tensor 63 % / MUFU 84 % busy, neither saturated; 8 stages of 64
-//     columns were worse still because an N=64 MMA reads 6 KB of shared memory in 32 clk, over the 128 B/clk port).
-//   * The walker block arrives pre-scaled by log2(e): accumulators hold a = eta*log2(e) and
-//       softplus(eta) = max(eta,0) + ln2*log2(1 + 2^-|a|),   sum_rows max(eta,0) = (sum eta + sum |eta|)/2,
-//     with sum_rows eta = (sum_rows x_row) . theta added analytically (k_glm_finish_tc).  The log is taken of a
-//     running PRODUCT of 16 factors (1+t) per chain, so an element costs MUFU.EX2(-|a|) + one FFMA + one FADD.
+//   * Persistent, warp-specialised CTA (1 per SM): warp 8 = TMA producer (3-stage ring of 32 KB X tiles),
+//     warp 9 = TMEM allocator + single-thread MMA issuer (4 accumulator stages of 128 columns),
+//     warps 0-15 = four epilogue groups (4 warps = 128 TMEM lanes each), group g drains accumulator stage g.
+//   * softplus(e) = max(e,0) + log(1 + exp(-|e|)); the log is taken of a running PRODUCT of 64 factors (1+t),
+//     so the epilogue costs one MUFU.EX2 per element and one MUFU.LG2 per 64 (MUFU is the binding unit).
 // There is no counterpart in the reference (its LOGFN loops over the dataset serially in every thread,
 // e.g. K/cuda/distributions/gaussian.cu:40-42); the arithmetic contract is the oracle's serial model.
 #pragma once
@@ -30,19 +25,16 @@
 namespace bay {
 namespace tc {
 
-constexpr int TILE = 128;                       // MMA M (walkers per block); rows per TMA tile
-constexpr int CN = 128;                         // MMA N: dataset rows per accumulator stage (one tile)
+constexpr int TILE = 128;                       // MMA M (walkers per block) and N (rows per tile)
 constexpr int KD = 64;                          // model dimension handled by this kernel
 constexpr int NSTAGE = 3;                       // X-tile ring
 constexpr int NACC = 4;                         // TMEM accumulator stages (4 x 128 columns = 512)
 constexpr int MAX_WB = 4;                       // walker blocks per launch (512 walkers)
 constexpr uint32_t TILE_BYTES = TILE * KD * 2;  // one bf16 plane of a tile: 16 KB
-constexpr int NGRP = 2;                         // epilogue groups (8 warps each); group g drains stages g, g+2
-constexpr int EPI_WARPS = 8 * NGRP;             // a group = 4 lane quarters x 2 column halves
-constexpr int THREADS = (EPI_WARPS + 2) * 32;   // 16 epilogue warps + TMA warp + MMA warp
+constexpr int NGRP = 4;                         // epilogue groups (4 warps each), one per accumulator stage
+constexpr int THREADS = (4 * NGRP + 2) * 32;    // 16 epilogue warps + TMA warp + MMA warp
 constexpr uint32_t IDESC =                      // kind::f16: D=f32, A=B=bf16, both K-major, N=128, M=128
-    (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CN >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
-constexpr float LOG2E = 1.4426950408889634f;
+    (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
 
 __host__ __device__ constexpr size_t smem_bytes(int nwb) {
     return 1024 /*alignment slack*/ + (size_t)nwb * 2 * TILE_BYTES + (size_t)NSTAGE * 2 * TILE_BYTES + 256;
@@ -99,25 +91,23 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// 2^x for x <= 0 on the FMA/ALU pipes (no MUFU): Cody-Waite split x = n + f, |f| <= 1/2, degree-5 minimax of 2^f
-// (max relative error 2.3e-7 in fp32 Horner form, i.e. the accuracy of MUFU.EX2), exponent patched in by integer add.
-__device__ __forceinline__ float ex2_poly(float x) {
-    const float xc = fmaxf(x, -126.0f);
-    const float r = xc + 12582912.0f;                 // 1.5 * 2^23: n = round(xc) lands in the low mantissa bits
-    const float f = xc - (r - 12582912.0f);
-    float p = 0.00132764654699713f;
-    p = fmaf(p, f, 0.009675540961325169f);
-    p = fmaf(p, f, 0.05550713464617729f);
-    p = fmaf(p, f, 0.24022120237350464f);
-    p = fmaf(p, f, 0.6931469440460205f);
-    p = fmaf(p, f, 1.0000001192092896f);
-    return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
-}
 __device__ __forceinline__ float lg2_approx(float x) {
     float y;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+
+#define BAY_TMEM_LD32(r, taddr)                                                                              \
+    asm volatile(                                                                                            \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                            \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                            \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"            \
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),      \
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), \
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),          \
+          "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),          \
+          "=r"(r[30]), "=r"(r[31])                                                                           \
+        : "r"(taddr) : "memory")
 
 #define BAY_TMEM_LD16(r, taddr)                                                                              \
     asm volatile(                                                                                            \
@@ -126,20 +116,16 @@ __device__ __forceinline__ float lg2_approx(float x) {
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),      \
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])  \
         : "r"(taddr) : "memory")
-#define BAY_TMEM_WAIT_LD() asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
 
 // ------------------------------------------------------------------ the kernel --
 // map_xh/map_xl: [rows][64] bf16 planes of the dataset; map_ah/map_al: [n_walkers][64] bf16 planes of the
-// walker block (hi, lo; already scaled by log2 e), origin at the first walker of this launch.
-// Work item = (tile, walker block): item = tile*NWB + wb, accumulator stage = item % 4, epilogue group = item % 2.
-// partial: [2*NGRP*gridDim.x][ldp] doubles; row ((NGRP*cta + group)*2 + column half), entry wb*128 + lane.
-// POLY: every fourth exp2 is evaluated by ex2_poly on the FMA pipe instead of MUFU.
-template <int NWB, bool POLY>
-__global__ void __launch_bounds__(THREADS, 1)
+// walker block (hi, lo), origin at the first walker of this launch.  partial: [NGRP*gridDim.x][ldp] doubles;
+// entry (NGRP*cta + group, wb*128 + lane) = that epilogue thread's sum.
+template <int NWB>
+__global__ void __launch_bounds__(THREADS, 1)  // NWB in {1, 2, 4}
 k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                 const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                 const uint32_t rows, const uint32_t n_tiles, double* __restrict__ partial, const uint32_t ldp) {
-    static_assert(NWB == 1 || NWB == 2 || NWB == 4, "walker blocks per launch");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* a_hi = smem;                                   // NWB tiles
@@ -158,11 +144,11 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < NACC; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+        for (int i = 0; i < NACC; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
         mbar_init(a_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == EPI_WARPS + 1) {   // TMEM: all 512 columns (one CTA per SM)
+    if (warp == 4 * NGRP + 1) {   // TMEM: all 512 columns (one CTA per SM)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -171,7 +157,7 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == EPI_WARPS) {
+    if (warp == 4 * NGRP) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             mbar_expect_tx(a_bar, NWB * 2 * TILE_BYTES);
@@ -188,7 +174,7 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                 tma_load_2d(b_base + (2 * s + 1) * TILE_BYTES, &map_xl, 0, row0, &full_bar[s]);
             }
         }
-    } else if (warp == EPI_WARPS + 1) {
+    } else if (warp == 4 * NGRP + 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             mbar_wait(a_bar, 0);
@@ -204,7 +190,7 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                     const uint32_t a = item % NACC, aph = (item / NACC) & 1u;
                     mbar_wait(&tempty_bar[a], aph ^ 1u);
                     tc_fence_after();
-                    const uint32_t d = tmem_base + a * CN;
+                    const uint32_t d = tmem_base + a * TILE;
                     const uint64_t ah = make_desc(smem_u32(a_hi + wb * TILE_BYTES));
                     const uint64_t al = make_desc(smem_u32(a_lo + wb * TILE_BYTES));
 #pragma unroll
@@ -220,22 +206,27 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         }
     } else {
         // ===================== epilogue groups =====================
+        // Group g drains accumulator stage g, i.e. items g, g+4, g+8, ... (item = tile*NWB + wb), which for
+        // NWB in {1,2,4} all belong to ONE walker block wb = g % NWB: a thread owns exactly one walker.
         // The loops are kept rolled on purpose: fully unrolled, the epilogue was ~100 KB of SASS and the
         // kernel stalled on instruction fetch (ncu: stall_no_inst).
-        const uint32_t grp = warp >> 3;                  // 8 warps per group
+        const uint32_t grp = warp >> 2;
         const uint32_t quarter = warp & 3;               // TMEM lanes 32*quarter .. +31
-        const uint32_t chalf = (warp >> 2) & 1u;         // columns 64*chalf .. +63 of the stage
+        const uint32_t wb_mine = grp % NWB;
+        const uint32_t tbase = tmem_base + ((quarter * 32u) << 16) + grp * TILE;
         const uint32_t n_items = my_tiles * NWB;
-        // Items of this group: item = grp, grp+2, ...; walker block wb = item % NWB.  For NWB = 4 a group
-        // alternates between two walker blocks (grp and grp+2): two accumulator pairs, selected by `sel`.
-        float hi0 = 0.f, lo0 = 0.f, hi1 = 0.f, lo1 = 0.f;   // two-float (compensated) sums
-        for (uint32_t item = grp; item < n_items; item += NGRP) {
-            const uint32_t a = item % NACC;
+        // The walker block arrives pre-scaled by log2(e), so the accumulators hold a = eta*log2(e) and
+        //   softplus(eta) = max(eta,0) + ln2*log2(1 + 2^-|a|),   sum_rows max(eta,0) = (sum eta + sum |eta|)/2,
+        // where sum_rows eta = (sum_rows x_row) . theta is added analytically by k_glm_finish_tc.  Per element that
+        // leaves MUFU.EX2(-|a|), one FFMA on the running product and one FADD on sum|a|.
+        // Rows that TMA zero-filled past the end of the dataset give a = 0 exactly: no |a|, factor 2 -> corrected
+        // by subtracting (TILE - valid) from the log2 sum.
+        float hi = 0.f, lo = 0.f;                        // two-float (compensated) sum over this thread's items
+        for (uint32_t item = grp; item < n_items; item += NACC) {
             const uint32_t it = item / NWB;
-            const uint32_t row0 = (blockIdx.x + it * gridDim.x) * TILE + chalf * 64u;
-            const uint32_t valid = rows > row0 ? min(64u, rows - row0) : 0u;
-            const uint32_t tbase = tmem_base + ((quarter * 32u) << 16) + a * CN + chalf * 64u;
-            mbar_wait(&tfull_bar[a], (item / NACC) & 1u);
+            const uint32_t row0 = (blockIdx.x + it * gridDim.x) * TILE;
+            const uint32_t valid = min((uint32_t)TILE, rows - row0);
+            mbar_wait(&tfull_bar[grp], (item / NACC) & 1u);
             tc_fence_after();
             // four independent (product, |a|-sum) chains; the next 16 columns are in flight while 16 are reduced
             float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, p0 = 1.f, p1 = 1.f, p2 = 1.f, p3 = 1.f;
@@ -245,60 +236,52 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                 for (int j = 0; j < 16; j += 4) {
                     const float e0 = fabsf(__uint_as_float(r[j])), e1 = fabsf(__uint_as_float(r[j + 1]));
                     const float e2 = fabsf(__uint_as_float(r[j + 2])), e3 = fabsf(__uint_as_float(r[j + 3]));
-                    const float t0 = ex2_approx(-e0), t1 = ex2_approx(-e1), t2 = ex2_approx(-e2);
-                    const float t3 = POLY ? ex2_poly(-e3) : ex2_approx(-e3);
+                    const float t0 = ex2_approx(-e0), t1 = ex2_approx(-e1), t2 = ex2_approx(-e2), t3 = ex2_approx(-e3);
                     p0 = fmaf(p0, t0, p0); p1 = fmaf(p1, t1, p1); p2 = fmaf(p2, t2, p2); p3 = fmaf(p3, t3, p3);
                     m0 += e0; m1 += e1; m2 += e2; m3 += e3;
                 }
             };
             BAY_TMEM_LD16(ra, tbase);
-            BAY_TMEM_WAIT_LD();
-            BAY_TMEM_LD16(rb, tbase + 16);
-            reduce(ra);
-            BAY_TMEM_WAIT_LD();
-            BAY_TMEM_LD16(ra, tbase + 32);
-            reduce(rb);
-            BAY_TMEM_WAIT_LD();
-            BAY_TMEM_LD16(rb, tbase + 48);
-            reduce(ra);
-            BAY_TMEM_WAIT_LD();
-            // every column of this warp's share is in registers: hand the accumulator back before the last reduction
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[a]);
-            reduce(rb);
-            // Rows that TMA zero-filled past the end of the dataset give a = 0 exactly: |a| = 0, factor 2 -> subtract
-            // one per such row from the log2 sum.  Item value (in units of ln2): sum log2(1+t) + sum|a|/2.
-            const float lg = (lg2_approx(p0 * p1) + lg2_approx(p2 * p3)) - (float)(64u - valid);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll 1
+            for (uint32_t c = 0; c < TILE; c += 32) {
+                BAY_TMEM_LD16(rb, tbase + c + 16);
+                reduce(ra);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c + 32 < TILE) {
+                    BAY_TMEM_LD16(ra, tbase + c + 32);
+                } else {
+                    // every column of the stage is in registers: hand the accumulator back before the last reduction
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[grp]);
+                }
+                reduce(rb);
+                if (c + 32 < TILE) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            }
+            // each chain holds 32 factors <= 2.  item value (in units of ln2): sum log2(1+t) + sum|a|/2
+            const float lg = (lg2_approx(p0 * p1) + lg2_approx(p2 * p3)) - (float)(TILE - valid);
             const float x = fmaf(0.5f, (m0 + m1) + (m2 + m3), lg);
-            const bool sel = (NWB == 4) && (((item / NGRP) & 1u) != 0u);
-            float& hi = sel ? hi1 : hi0;
-            float& lo = sel ? lo1 : lo0;
             const float s = hi + x;                      // Knuth two-sum: (hi, lo) += x without fp64 (DADD is slow here)
             const float bp = s - hi;
             lo += (hi - (s - bp)) + (x - bp);
             hi = s;
         }
-        const double v0 = ((double)hi0 + (double)lo0) * 0.6931471805599453;
-        const double v1 = ((double)hi1 + (double)lo1) * 0.6931471805599453;
-        // partial row (cta, group, column half); walker blocks this thread never saw get 0
-        const size_t base = (size_t)((NGRP * blockIdx.x + grp) * 2 + chalf) * ldp + quarter * 32 + lane;
+        const double acc64 = ((double)hi + (double)lo) * 0.6931471805599453;
+        const size_t base = (size_t)(NGRP * blockIdx.x + grp) * ldp + quarter * 32 + lane;
 #pragma unroll
-        for (int wb = 0; wb < NWB; wb++) {
-            double v = 0.0;
-            if (NWB == 4) v = (wb == (int)grp) ? v0 : ((wb == (int)grp + 2) ? v1 : 0.0);
-            else v = (wb == (int)(grp % NWB)) ? v0 : 0.0;
-            partial[base + wb * TILE] = v;
-        }
+        for (int wb = 0; wb < NWB; wb++) partial[base + wb * TILE] = (wb == (int)wb_mine) ? acc64 : 0.0;
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == EPI_WARPS + 1) {
+    if (warp == 4 * NGRP + 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
+
+constexpr float LOG2E = 1.4426950408889634f;
 
 // points (SoA, dim 64 x n, pitch) -> bf16 hi/lo planes [n][64] (row = walker) of theta * log2(e), the A operand
 __global__ void k_glm_split_points(const float* __restrict__ pts, uint32_t pitch, uint32_t n,
