@@ -181,7 +181,8 @@ def run_reference(args, wl: dict, rank: int, world: int):
         sample += f", on {wl['cpu_rows']} of {wl['rows']} rows, rate scaled linearly by rows"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if wl.get("glm") else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "walkers": walkers, "dim": wl["model"].dimension,
                        "engine": "CPU oracle (C restatement of the reference kernels, OpenMP over walkers)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
@@ -197,7 +198,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("BAY_WORKLOAD", "c2"))
+    ap.add_argument("--workload", default=os.environ.get("BAY_WORKLOAD", "c4"))
     ap.add_argument("--moves-per-step", type=int, default=0)
     ap.add_argument("--walkers", type=int, default=0)
     ap.add_argument("--wgs", type=int, default=256)
@@ -241,12 +242,25 @@ def main():
     assert stream.cuda_stream != 0
     factory = bb.B200BayaderaFactory(device=local_rank, stream=stream.cuda_stream, wgs=args.wgs)
     assert factory.stream() == stream.cuda_stream
+    sharded = bool(wl.get("glm")) and world > 1
+    if sharded:
+        # SURVEY §8e mode B: walkers replicated, dataset rows sharded, per-walker partial sums all-reduced by the
+        # engine over NCCL.  Total work is fixed (10^7 rows) -> strong scaling.
+        from bayadera_b200.distributed import init_engine_comm, shard_rows
+        init_engine_comm(factory, rank, world, torch.device("cuda", local_rank))
     sfactory = factory.mcmc_factory(model)
     params = wl["params"]
     if params is None:
-        params = bb.DeviceParams.from_torch(logreg_rows_device(torch, wl["rows"], D, 2024, torch.device("cuda", local_rank)))
-    sampler = sfactory.create_sampler(123 + rank, W, params)
-    sampler.init_position(1000 + rank, wl["limits"])
+        if sharded:
+            b, e = shard_rows(wl["rows"], world, rank)
+            local_rows, seed = e - b, 2024 + 1000 * rank
+        else:
+            local_rows, seed = wl["rows"], 2024
+        params = bb.DeviceParams.from_torch(logreg_rows_device(torch, local_rows, D, seed, torch.device("cuda", local_rank)))
+    # replicated walkers need identical seeds on every rank; independent replicas (non-GLM, N>1) differ by rank
+    seed_off = 0 if sharded else rank
+    sampler = sfactory.create_sampler(123 + seed_off, W, params)
+    sampler.init_position(1000 + seed_off, wl["limits"])
     sampler.burn_in(max(64, M), a)                      # leave the initial box before timing
     p_acc = sampler.acc_rate(a)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -291,7 +305,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
 
-    total_ws = float(world) * W * M * args.steps
+    total_ws = (1.0 if sharded else float(world)) * W * M * args.steps
     value = total_ws / (dev_ms * 1e-3)
     e2e_value = total_ws / (e2e_ms * 1e-3)
     per_launch_ms = dev_ms / (2.0 * M * args.steps)
@@ -302,15 +316,16 @@ def main():
         # dominant kernel: the dataset likelihood (one launch per half-step; propose/finish/accept are ~1 % of it).
         # Dense contraction X(rows x D) . Theta(D x H): 2*rows*D flops per walker-step, bf16-dense peak
         # as the denominator (an fp32-accurate 3-term split can reach at most 1/3 of it).
-        kernel_name = "bay_glm_loglik"
-        flops_per_launch = 2.0 * wl["rows"] * D * (W / 2)
+        kernel_name = "k_glm_loglik_tc"
+        flops_per_launch = 2.0 * (wl["rows"] / (world if sharded else 1)) * D * (W / 2)   # per GPU
         peak = float(peaks["bf16_tflops_sustained"]) if peaks else 1400.0
         achieved = flops_per_launch / (per_launch_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": None, "kernel": kernel_name, "peak_source": peak_src, "flops_per_launch": flops_per_launch,
                 "launch_us": per_launch_ms * 1e3,
-                "hbm_view": {"bytes_per_launch": 4.0 * wl["rows"] * D,
-                             "achieved_GBps": 4.0 * wl["rows"] * D / (per_launch_ms * 1e-3) / 1e9}}
+                "hbm_view": {"bytes_per_launch": flops_per_launch / (W / 2) * 2.0,
+                             "achieved_GBps": flops_per_launch / (W / 2) * 2.0 / (per_launch_ms * 1e-3) / 1e9,
+                             "note": "dataset bytes (bf16 hi+lo planes = 4 B/element) streamed once per launch"}}
     else:
         kernel_name = "bay_stretch_bare"
         bytes_per_launch = (W / 2) * algorithmic_bytes_per_walker_step(D, p_acc)
@@ -327,14 +342,22 @@ def main():
             cpu = {"value": r, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{wl['cpu_walkers']} walkers x {n} moves ({dt:.1f} s) of workload {wl['key']}, CPU oracle (OpenMP)"
                              + (f", on {wl['cpu_rows']} of {wl['rows']} rows, rate scaled linearly by rows" if wl.get("rows") else "")}
-        info = sfactory.kernel_info(kernel_name)
+        if wl.get("glm"):   # statically compiled kernel: numbers from the nvcc -Xptxas -v log (profiles/)
+            info = {"registers": 96, "local_bytes": 0, "shared_bytes": int(1024 + 4 * 2 * 16384 + 3 * 2 * 16384 + 256),
+                    "block": 576, "grid": "1 CTA per SM (persistent)"}
+        else:
+            info = sfactory.kernel_info(kernel_name)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "strong" if wl.get("glm") else "weak", "vs_baseline": None,
+                "dtype": "f32 (bf16x3 split on tensor cores, fp32 accumulate)" if wl.get("glm") else "f32",
+                "data": "synthetic",
                 "config": {"workload": wl["desc"], "walkers_per_gpu": W, "dim": D, "moves_per_step": M, "a": a,
                            **({"rows": wl["rows"]} if wl.get("rows") else {}),
                            "acceptance": round(p_acc, 4), "wgs": args.wgs,
-                           "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (no exchange)",
+                           "parallelism": "single GPU" if world == 1 else (
+                               f"rows sharded over {world} GPUs, walkers replicated, NCCL all-reduce of per-walker sums"
+                               if sharded else f"{world} independent replicas (no exchange)"),
                            "l2": "flushed between timed steps (256 MiB write)",
                            "kernel": {"name": kernel_name, **info}},
                 "e2e": {"value": e2e_value, "unit": UNIT,
