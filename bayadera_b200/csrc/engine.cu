@@ -25,6 +25,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -287,6 +288,7 @@ struct bay_sampler {
     bool glm_tc = false;
     __nv_bfloat16 *glm_xh = nullptr, *glm_xl = nullptr, *glm_ah = nullptr, *glm_al = nullptr;
     CUtensorMap glm_map_xh, glm_map_xl;
+    std::map<uint64_t, std::pair<CUtensorMap, CUtensorMap>> glm_amaps;   // (first walker, count) -> (hi, lo) maps
     // host-side counters: G/:282-287, 340-400
     int32_t bare_seed = 0, move_seed = 0;
     uint32_t bare_counter = 0, move_counter = 0;

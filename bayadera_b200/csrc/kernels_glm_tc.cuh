@@ -295,18 +295,21 @@ __global__ void k_glm_split_points(const float* __restrict__ pts, uint32_t pitch
     lo[e] = __float2bfloat16_rn(x - __bfloat162float(h));
 }
 
-// sp[k] = sum over the kernel's partial rows (fixed order) + (ln2/2) * sx . (theta_k * log2 e): the analytic
-// sum_rows eta term of  sum max(eta,0) = (sum eta + sum |eta|) / 2.  sx = column sums of the LOCAL rows.
+// sp[k] = sum over the kernel's partial rows + (ln2/2) * sx . (theta_k * log2 e): the analytic sum_rows eta term of
+// sum max(eta,0) = (sum eta + sum |eta|) / 2.  sx = column sums of the LOCAL rows.  One warp per walker: lanes
+// stride over the partial rows, then a fixed shuffle tree (deterministic: same order on every run and rank).
 __global__ void k_glm_finish_tc(uint32_t n, uint32_t chunks, uint32_t ldp, const double* __restrict__ partial,
                                 const double* __restrict__ sx, const float* __restrict__ pts, uint32_t pitch,
                                 double* __restrict__ sp) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (k >= n) return;
     double s = 0.0;
-    for (uint32_t c = 0; c < chunks; c++) s += partial[(size_t)c * ldp + k];
-    double dot = 0.0;
-    for (uint32_t i = 0; i < KD; i++) dot += sx[i] * (double)__fmul_rn(pts[(size_t)i * pitch + k], LOG2E);
-    sp[k] = s + 0.5 * 0.6931471805599453 * dot;
+    for (uint32_t c = lane; c < chunks; c += 32) s += partial[(size_t)c * ldp + k];
+    for (uint32_t i = lane; i < KD; i += 32)
+        s += 0.5 * 0.6931471805599453 * sx[i] * (double)__fmul_rn(pts[(size_t)i * pitch + k], LOG2E);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) sp[k] = s;
 }
 
 // dataset rows [y, x_1..x_64] (stride 65) -> bf16 hi/lo planes [rows][64]

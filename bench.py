@@ -62,7 +62,7 @@ def workload(name: str):
         d, rows = 64, 10 ** 7
         m = models.logistic_regression_model(d)
         return dict(key="c4", desc="Bayesian logistic regression, D=64, 10^7 synthetic rows (BASELINE configs[3])",
-                    model=m, params=None, limits=m.limits_array(), walkers=1024, moves=1, a=1.2,
+                    model=m, params=None, limits=m.limits_array(), walkers=4096, moves=1, a=1.2,
                     cpu_walkers=512, rows=rows, cpu_rows=4000, glm=True)
     raise SystemExit(f"unknown workload {name}")
 
@@ -316,15 +316,19 @@ def main():
         # dominant kernel: the dataset likelihood (one launch per half-step; propose/finish/accept are ~1 % of it).
         # Dense contraction X(rows x D) . Theta(D x H): 2*rows*D flops per walker-step, bf16-dense peak
         # as the denominator (an fp32-accurate 3-term split can reach at most 1/3 of it).
+        # one launch handles up to 512 walkers against all local rows; a half-step of H = W/2 walkers is ceil(H/512)
+        # back-to-back launches, so the per-launch duration is the half-step time divided by that count
         kernel_name = "k_glm_loglik_tc"
-        flops_per_launch = 2.0 * (wl["rows"] / (world if sharded else 1)) * D * (W / 2)   # per GPU
+        n_groups = -(-(W // 2) // 512)
+        per_launch_ms = per_launch_ms / n_groups
+        flops_per_launch = 2.0 * (wl["rows"] / (world if sharded else 1)) * D * min(W // 2, 512)   # per GPU
         peak = float(peaks["bf16_tflops_sustained"]) if peaks else 1400.0
         achieved = flops_per_launch / (per_launch_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": None, "kernel": kernel_name, "peak_source": peak_src, "flops_per_launch": flops_per_launch,
                 "launch_us": per_launch_ms * 1e3,
-                "hbm_view": {"bytes_per_launch": flops_per_launch / (W / 2) * 2.0,
-                             "achieved_GBps": flops_per_launch / (W / 2) * 2.0 / (per_launch_ms * 1e-3) / 1e9,
+                "hbm_view": {"bytes_per_launch": flops_per_launch / min(W // 2, 512) * 2.0,
+                             "achieved_GBps": flops_per_launch / min(W // 2, 512) * 2.0 / (per_launch_ms * 1e-3) / 1e9,
                              "note": "dataset bytes (bf16 hi+lo planes = 4 B/element) streamed once per launch"}}
     else:
         kernel_name = "bay_stretch_bare"
@@ -344,7 +348,7 @@ def main():
                              + (f", on {wl['cpu_rows']} of {wl['rows']} rows, rate scaled linearly by rows" if wl.get("rows") else "")}
         if wl.get("glm"):   # statically compiled kernel: numbers from the nvcc -Xptxas -v log (profiles/)
             info = {"registers": 96, "local_bytes": 0, "shared_bytes": int(1024 + 4 * 2 * 16384 + 3 * 2 * 16384 + 256),
-                    "block": 576, "grid": "1 CTA per SM (persistent)"}
+                    "block": 576, "grid": "1 CTA per SM (persistent)", "launches_per_half_step": -(-(W // 2) // 512)}
         else:
             info = sfactory.kernel_info(kernel_name)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
