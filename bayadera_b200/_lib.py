@@ -85,6 +85,8 @@ SIGNATURES = {
     "bay_info": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "bay_get_state": (C.c_int, [_vp, _vp, _vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i64)]),
     "bay_set_state": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i64, _i64]),
+    "bay_get_state64": (C.c_int, [_vp, _vp, _vp]),
+    "bay_set_state64": (C.c_int, [_vp, _vp, _vp]),
     "bay_dataset_mean": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _i64, _i64, _f32]),
     "bay_dataset_variance": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _i64, _i64, _f32]),
     "bay_dataset_histogram": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),

@@ -272,6 +272,7 @@ struct bay_sampler {
     float* ranks = nullptr;                   // wgs x D
     double* macc = nullptr;                   // D x 2
     float* vec_d = nullptr;                   // 4 x D scratch
+    float* stage = nullptr;                   // D x W AoS staging for state hand-off (lazy)
     // GLM path: repacked dataset, proposals and double-precision log-densities
     uint64_t glm_rows = 0;                    // local rows (this rank's shard)
     float* glm_x = nullptr;                   // rows x D row-major
@@ -629,7 +630,7 @@ extern "C" int bay_sampler_release(bay_sampler* s) {
     if (s->own_params) cudaFree(s->params);
     glm_release(s);
     void* bufs[] = {s->xs, s->lp, s->accept, s->blk_sums, s->accept_total, s->means, s->hist_counts, s->mm,
-                    s->limits, s->pdf, s->ranks, s->macc, s->vec_d};
+                    s->limits, s->pdf, s->ranks, s->macc, s->vec_d, s->stage};
     for (void* b : bufs) if (b) cudaFree(b);
     delete s;
     return BAY_OK;

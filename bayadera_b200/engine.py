@@ -317,6 +317,19 @@ class B200Stretch:
                                     pick(bare_counter, 2), pick(move_counter, 3)))
         return self
 
+    def get_state64(self, xs_out: Optional[np.ndarray] = None, logfn_out: Optional[np.ndarray] = None):
+        """Positions (W x DIM fp32) and log-densities in double; optional preallocated (e.g. pinned) outputs."""
+        xs = np.zeros((self.walker_count, self.DIM), dtype=np.float32) if xs_out is None else xs_out
+        lp = np.zeros(self.walker_count, dtype=np.float64) if logfn_out is None else logfn_out
+        check(self._L.bay_get_state64(self._h, ptr(xs), ptr(lp)))
+        return xs, lp
+
+    def set_state64(self, xs, logfn64) -> "B200Stretch":
+        x = _f32(xs).reshape(-1)
+        l = np.ascontiguousarray(logfn64, dtype=np.float64).reshape(-1)
+        check(self._L.bay_set_state64(self._h, ptr(x), ptr(l)))
+        return self
+
     def release(self) -> None:
         if self._h:
             self._L.bay_sampler_release(self._h)

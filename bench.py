@@ -284,19 +284,17 @@ def main():
     clk = clocks.finish()
     dev_ms = sum(s.elapsed_time(e) for s, e in ev)
 
-    # ---- e2e: host ensemble -> device, advance, device -> host, through the C-ABI ----
-    state = sampler.get_state()
-    xs_host = torch.from_numpy(state["xs"]).pin_memory().numpy()
-    lp_host = torch.from_numpy(state["logfn"]).pin_memory().numpy()
-    sampler.set_state(xs=xs_host, logfn=lp_host)
+    # ---- e2e: host ensemble -> device, advance, device -> host, through the C-ABI with pinned HOST buffers ----
+    xs0, lp0 = sampler.get_state64()
+    xs_host = torch.from_numpy(xs0).pin_memory().numpy()
+    lp_host = torch.from_numpy(lp0).pin_memory().numpy()
+    sampler.set_state64(xs_host, lp_host)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        sampler.set_state(xs=xs_host, logfn=lp_host)
+        sampler.set_state64(xs_host, lp_host)          # H2D: positions (fp32) + log-densities (fp64)
         sampler.burn_in(M, a)
-        out = sampler.get_state()
-        xs_host[:] = out["xs"]
-        lp_host[:] = out["logfn"]
+        sampler.get_state64(xs_host, lp_host)          # D2H into the same pinned buffers
     barrier()
     e2e_s = time.perf_counter() - t0
 
@@ -367,7 +365,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT,
                         "h2d_bytes_per_step": int(xs_host.nbytes + lp_host.nbytes),
                         "d2h_bytes_per_step": int(xs_host.nbytes + lp_host.nbytes),
-                        "what": "bay_set_state(host ensemble) + burn-in! + bay_get_state(host) per step"},
+                        "what": "bay_set_state64(pinned host ensemble) + burn-in! + bay_get_state64(pinned host) per step"},
                 "gpu_launches": int(launches),
                 "roofline": roof,
                 "cpu_baseline": cpu, "clocks": clk}

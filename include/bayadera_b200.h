@@ -152,6 +152,10 @@ int bay_get_state(bay_sampler *s, float *xs_host, float *logfn_host, int32_t *ba
                   int32_t *move_seed, int64_t *bare_counter, int64_t *move_counter);
 int bay_set_state(bay_sampler *s, const float *xs_host, const float *logfn_host /* NULL: recompute */,
                   int32_t bare_seed, int32_t move_seed, int64_t bare_counter, int64_t move_counter);
+/* same hand-off with the log-densities in double: samplers of row-additive (GLM) models carry log-densities of
+ * ~ -1e6..-1e7 whose O(1) differences fp32 cannot hold; with these nothing is recomputed on restore. */
+int bay_get_state64(bay_sampler *s, float *xs_host, double *logfn64_host);
+int bay_set_state64(bay_sampler *s, const float *xs_host, const double *logfn64_host);
 
 /* ---- DatasetEngine / EstimateEngine on an arbitrary matrix, P/:71-73, 82-84; G/:145-228 ----
  * data: m x n, element (row, col) at data[offset + ld*col + row]. */
