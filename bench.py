@@ -98,7 +98,7 @@ def algorithmic_bytes_per_walker_step(dim: int, p_acc: float) -> float:
 
 # --------------------------------------------------------------------------------------------- clocks --
 class ClockSampler(threading.Thread):
-    """Samples SM clock and clock-event reasons through NVML every 100 ms while the timed region runs."""
+    """Samples SM clock and clock-event reasons through NVML every 20 ms while the timed region runs."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
@@ -129,7 +129,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._halt.wait(0.1)
+            self._halt.wait(0.02)
 
     def finish(self) -> dict:
         self._halt.set()
@@ -195,7 +195,7 @@ def run_reference(args, wl: dict, rank: int, world: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("BAY_WORKLOAD", "c4"))
