@@ -245,6 +245,8 @@ struct bay_model {
     // GLM (row-additive Bernoulli-logit) path, present iff `glm`
     CUfunction f_glm_propose = nullptr, f_glm_loglik = nullptr, f_glm_lp_init = nullptr, f_glm_accept = nullptr;
     bool glm = false;
+    bool mirror = false;   // AoS mirror of the ensemble for the partner gather (DIM >= 4, non-GLM)
+    int dima = 1;          // mirror row length: DIM rounded up to a multiple of 4
     int dim = 1, params_size = 0;
     uint32_t flags = 0;
     int block = 128;  // bare/logfn block size
@@ -260,6 +262,7 @@ struct bay_sampler {
     uint32_t data_len = 0, params_len = 0;
     float* xs = nullptr;  // D x W SoA, pitch W
     float* lp = nullptr;  // W
+    float* xa = nullptr;  // W x dima AoS mirror (only if m->mirror)
     uint32_t* accept = nullptr;               // G
     float* blk_sums = nullptr;                // D x G
     unsigned long long* accept_total = nullptr;  // 1
@@ -386,6 +389,15 @@ extern "C" int bay_engine_comm_init(bay_engine* e, const uint8_t id[128], int nr
 }
 
 // ------------------------------------------------------------------- model --
+// The AoS mirror pays off once a walker spans several 32-byte sectors; GLM models gather only H rows per half-step.
+// BAY_MIRROR=0 in the environment disables it (A/B measurements).
+static bool model_wants_mirror(int dim, uint32_t flags) {
+    if (dim < 4) return false;
+    if ((flags & BAY_MODEL_GLM_LOGISTIC) && dim % 4 == 0) return false;
+    const char* env = getenv("BAY_MIRROR");
+    return !(env && env[0] == '0');
+}
+
 // NVRTC step shared by bay_model_compile and bay_model_compile_check.
 // gtx-stretch-factory (G/:747-757): model sources first, engine kernels after;
 // stretch-options (G/:630-633) retargeted to sm_100a.
@@ -408,6 +420,10 @@ static int nvrtc_build(const char* const* srcs, int nsrc, const char* logfn_name
                                      "-DLOGFN=" + std::string(logfn_name), "-DDIM=" + std::to_string(dim),
                                      "-DWGS=" + std::to_string(wgs), "-DBAY_BLOCK=" + std::to_string(block)};
     if (flags & BAY_MODEL_FAST_MATH) opts.push_back("-use_fast_math");
+    if (model_wants_mirror(dim, flags)) {
+        opts.push_back("-DBAY_MIRROR=1");
+        opts.push_back("-DBAY_DIMA=" + std::to_string((dim + 3) / 4 * 4));
+    }
     if (verbose) opts.push_back("--ptxas-options=-v");
     std::vector<const char*> copts;
     for (auto& o : opts) copts.push_back(o.c_str());
@@ -465,6 +481,8 @@ extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsr
     m->params_size = params_size;
     m->flags = flags;
     m->block = bare_block_for(dim);
+    m->mirror = model_wants_mirror(dim, flags);
+    m->dima = (dim + 3) / 4 * 4;
 
     CUresult cr = g_cu.ModuleLoadData(&m->mod, cubin.data());
     if (cr != CUDA_SUCCESS) {
@@ -543,6 +561,10 @@ static int sampler_alloc(bay_sampler* s) {
     const size_t W = (size_t)s->W, D = (size_t)s->D, wgs = (size_t)e->wgs;
     CK(cudaMalloc(&s->xs, sizeof(float) * D * W));
     CK(cudaMalloc(&s->lp, sizeof(float) * W));
+    if (s->m->mirror) {
+        CK(cudaMalloc(&s->xa, sizeof(float) * W * (size_t)s->m->dima));
+        CK(cudaMemsetAsync(s->xa, 0, sizeof(float) * W * (size_t)s->m->dima, e->stream));
+    }
     CK(cudaMalloc(&s->accept, sizeof(uint32_t) * s->G));
     CK(cudaMalloc(&s->blk_sums, sizeof(float) * D * s->G));
     CK(cudaMalloc(&s->accept_total, sizeof(unsigned long long)));
@@ -630,7 +652,7 @@ extern "C" int bay_sampler_release(bay_sampler* s) {
     if (s->own_params) cudaFree(s->params);
     glm_release(s);
     void* bufs[] = {s->xs, s->lp, s->accept, s->blk_sums, s->accept_total, s->means, s->hist_counts, s->mm,
-                    s->limits, s->pdf, s->ranks, s->macc, s->vec_d, s->stage};
+                    s->limits, s->pdf, s->ranks, s->macc, s->vec_d, s->stage, s->xa};
     for (void* b : bufs) if (b) cudaFree(b);
     delete s;
     return BAY_OK;
@@ -644,6 +666,17 @@ extern "C" int bay_init(bay_sampler* s, int32_t seed) {
     s->beta = 1.0f;
     s->bare_counter = 0;
     s->move_seed = seed;
+    return BAY_OK;
+}
+
+// rebuild the AoS mirror from the SoA state (after init / state hand-off)
+static int mirror_sync(bay_sampler* s) {
+    if (!s->m->mirror) return BAY_OK;
+    bay_engine* e = s->m->e;
+    dim3 grid(cdiv((uint64_t)s->W, 32), cdiv((uint64_t)s->D, 32)), block(32, 8);
+    bay::k_soa_to_aos<<<grid, block, 0, e->stream>>>(s->xs, (uint32_t)s->W, (uint32_t)s->D, (uint64_t)s->W, s->xa,
+                                                     (uint32_t)s->m->dima);
+    CKLAUNCH();
     return BAY_OK;
 }
 
@@ -665,6 +698,7 @@ extern "C" int bay_init_position_uniform(bay_sampler* s, int32_t seed, const flo
     bay::k_init_walkers<<<cdiv(n4, 256), 256, 0, e->stream>>>(n4, (uint32_t)s->D, (uint32_t)seed, s->limits, s->xs,
                                                            (uint32_t)s->W);
     CKLAUNCH();
+    TRY(mirror_sync(s));
     TRY(launch_logfn_all(s));
     // limits_host may be pageable: the async copy above is staged before return, but be safe
     CK(cudaStreamSynchronize(e->stream));
@@ -679,6 +713,7 @@ extern "C" int bay_init_position_from(bay_sampler* s, const bay_sampler* other) 
     bay_engine* e = s->m->e;
     TRY(use_device(e));
     CK(cudaMemcpyAsync(s->xs, other->xs, sizeof(float) * (size_t)s->D * s->W, cudaMemcpyDeviceToDevice, e->stream));
+    TRY(mirror_sync(s));
     TRY(launch_logfn_all(s));
     s->iterations = 0;
     return BAY_OK;
@@ -692,8 +727,10 @@ static int half_bare(bay_sampler* s, int half, uint32_t seed, uint32_t tag, floa
     float* act = s->xs + (half ? s->H : 0);
     float* cmp = s->xs + (half ? 0 : s->H);
     float* lp = s->lp + (half ? s->H : 0);
+    float* cmp_a = s->xa ? s->xa + (size_t)(half ? 0 : s->H) * m->dima : nullptr;
+    float* act_a = s->xa ? s->xa + (size_t)(half ? s->H : 0) * m->dima : nullptr;
     void* args[] = {&K, &seed, &tag, &s->data_len, &s->params_len, &s->params, &cmp, &act, &pitch, &lp,
-                    &cA, &cB, &cC, &beta, &step};
+                    &cA, &cB, &cC, &beta, &step, &cmp_a, &act_a};   // the last two only exist with BAY_MIRROR
     return launch(m->e, m->f_bare, cdiv(K, m->block), m->block, args);
 }
 
@@ -705,8 +742,10 @@ static int half_accu(bay_sampler* s, int half, uint32_t seed, uint32_t tag, floa
     float* act = s->xs + (half ? s->H : 0);
     float* cmp = s->xs + (half ? 0 : s->H);
     float* lp = s->lp + (half ? s->H : 0);
+    float* cmp_a = s->xa ? s->xa + (size_t)(half ? 0 : s->H) * m->dima : nullptr;
+    float* act_a = s->xa ? s->xa + (size_t)(half ? s->H : 0) * m->dima : nullptr;
     void* args[] = {&K, &seed, &tag, &s->data_len, &s->params_len, &s->params, &cmp, &act, &pitch, &lp,
-                    &s->accept, &s->blk_sums, &cA, &cB, &cC, &step, &accumulate};
+                    &s->accept, &s->blk_sums, &cA, &cB, &cC, &step, &accumulate, &cmp_a, &act_a};
     return launch(m->e, m->f_accu, s->G, m->e->wgs, args);
 }
 

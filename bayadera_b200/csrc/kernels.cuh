@@ -54,9 +54,9 @@ __global__ void k_init_walkers(uint32_t n4, uint32_t dim, uint32_t seed,
 }
 
 // ------------------------------------------------------------- transposes --
-// SoA (dim x n, pitch) -> AoS column-major dim x n (ld = dim): out[w*dim + d]
+// SoA (dim x n, pitch) -> AoS column-major dim x n with leading dimension ld: out[w*ld + d]
 __global__ void k_soa_to_aos(const float* __restrict__ xs, uint32_t pitch, uint32_t dim,
-                             uint64_t n, float* __restrict__ out) {
+                             uint64_t n, float* __restrict__ out, uint32_t ld) {
     __shared__ float tile[32][33];
     const uint64_t w0 = (uint64_t)blockIdx.x * 32;
     const uint32_t d0 = blockIdx.y * 32;
@@ -69,7 +69,7 @@ __global__ void k_soa_to_aos(const float* __restrict__ xs, uint32_t pitch, uint3
     for (uint32_t r = threadIdx.y; r < 32; r += blockDim.y) {
         const uint64_t w = w0 + r;
         const uint32_t d = d0 + threadIdx.x;
-        if (d < dim && w < n) out[w * dim + d] = tile[threadIdx.x][r];
+        if (d < dim && w < n) out[w * ld + d] = tile[threadIdx.x][r];
     }
 }
 

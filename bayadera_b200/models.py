@@ -314,22 +314,37 @@ def logistic_regression_model(d: int = 64, prior_sd: float = 10.0) -> DeviceMode
 def mvn_model(d: int = 100) -> DeviceModel:
     """config 5: d-dimensional correlated Gaussian N(mu, Sigma).
 
-    params = [mu (d) | U packed row-major upper triangle (d(d+1)/2)] with Sigma^-1 = U^T U,
-    so logpdf = -0.5 * |U (x - mu)|^2 costs d(d+1)/2 FMAs instead of d^2."""
+    params = [mu (d) | U (d x d row-major, upper triangular, zeros below the diagonal)] with Sigma^-1 = U^T U,
+    so logpdf = -0.5 * |U (x - mu)|^2.  d must be a multiple of 4: rows of U and the centred point are read as
+    aligned float4 (one 16-byte load per 4 FMAs); only the blocks on or right of the diagonal are visited
+    (~d(d+4)/2 FMAs instead of d^2)."""
+    if d % 4:
+        raise ValueError("mvn_model needs a dimension that is a multiple of 4")
+    q = d // 4
     body = f"""
-        REAL c[{d}];
-        for (uint32_t i = 0; i < {d}; i++) c[i] = x[i] - params[i];
-        const REAL* U = &params[{d}];
+        float4 c[{q}];
+        for (uint32_t i = 0; i < {q}; i++) {{
+            c[i].x = x[4 * i] - params[4 * i];
+            c[i].y = x[4 * i + 1] - params[4 * i + 1];
+            c[i].z = x[4 * i + 2] - params[4 * i + 2];
+            c[i].w = x[4 * i + 3] - params[4 * i + 3];
+        }}
+        const float4* U = (const float4*)&params[{d}];
         REAL acc = 0.0f;
-        uint32_t at = 0;
         for (uint32_t i = 0; i < {d}; i++) {{
-            REAL r = 0.0f;
-            for (uint32_t j = i; j < {d}; j++) r += U[at++] * c[j];
+            REAL r0 = 0.0f, r1 = 0.0f;
+            for (uint32_t j = i / 4; j < {q}; j++) {{
+                const float4 u = U[i * {q} + j];
+                const float4 v = c[j];
+                r0 += u.x * v.x + u.y * v.y;
+                r1 += u.z * v.z + u.w * v.w;
+            }}
+            const REAL r = r0 + r1;
             acc += r * r;
         }}
         return -0.5f * acc;"""
     src = distribution_source(f"mvn{d}_mcmc_logpdf", body)
-    return DeviceModel(f"mvn{d}", (src,), f"mvn{d}_mcmc_logpdf", d, d + d * (d + 1) // 2,
+    return DeviceModel(f"mvn{d}", (src,), f"mvn{d}_mcmc_logpdf", d, d + d * d,
                        _lim(*([(-30.0, 30.0)] * d)), f"mvn{d}_mcmc_logpdf")
 
 
@@ -343,5 +358,4 @@ def mvn_params(d: int = 100, seed: int = 5) -> Tuple[np.ndarray, np.ndarray, np.
     prec = (q / ev) @ q.T
     u = np.linalg.cholesky(prec).T          # prec = U^T U, U upper triangular
     mu = np.arange(d, dtype=np.float64) / 10.0
-    packed = np.concatenate([u[i, i:] for i in range(d)])
-    return np.concatenate([mu, packed]).astype(np.float32), mu, sigma
+    return np.concatenate([mu, np.triu(u).reshape(-1)]).astype(np.float32), mu, sigma

@@ -82,6 +82,7 @@ _PRELUDE = """#include <math.h>
 #define REAL float
 #define REAL2 float2
 #define ACCUMULATOR float
+struct alignas(16) float4 { float x, y, z, w; };   /* CUDA built-in vector type used by some models */
 """
 _model_cache: dict = {}
 

@@ -88,9 +88,6 @@ def test_parameter_vectors():
     p = models.beta_params(3, 2)
     assert p.dtype == np.float32 and np.isclose(p[2], np.log(12.0), rtol=1e-6)   # -lbeta(3,2) = log 12
     v, mu, sigma = models.mvn_params(8, seed=1)
-    u = np.zeros((8, 8))
-    at = 8
-    for i in range(8):
-        u[i, i:] = v[at:at + 8 - i]
-        at += 8 - i
+    u = v[8:].reshape(8, 8).astype(np.float64)
+    assert np.allclose(u, np.triu(u))
     assert np.allclose(np.linalg.inv(u.T @ u), sigma, rtol=2e-3, atol=1e-3)
