@@ -241,7 +241,8 @@ struct bay_engine {
 struct bay_model {
     bay_engine* e = nullptr;
     CUmodule mod = nullptr;
-    CUfunction f_bare = nullptr, f_accu = nullptr, f_logfn = nullptr;
+    CUfunction f_bare = nullptr, f_accu = nullptr, f_logfn = nullptr, f_loop = nullptr;
+    int loop_capacity = 0;   // co-resident CTAs of the persistent step-loop kernel on this device
     // GLM (row-additive Bernoulli-logit) path, present iff `glm`
     CUfunction f_glm_propose = nullptr, f_glm_loglik = nullptr, f_glm_lp_init = nullptr, f_glm_accept = nullptr;
     bool glm = false;
@@ -263,6 +264,9 @@ struct bay_sampler {
     float* xs = nullptr;  // D x W SoA, pitch W
     float* lp = nullptr;  // W
     float* xa = nullptr;  // W x dima AoS mirror (only if m->mirror)
+    unsigned int* loop_bar = nullptr;   // grid-barrier words of the persistent step loop
+    float* loop_betas = nullptr;        // per-step inverse temperatures (anneal!)
+    int64_t loop_betas_cap = 0;
     uint32_t* accept = nullptr;               // G
     float* blk_sums = nullptr;                // D x G
     unsigned long long* accept_total = nullptr;  // 1
@@ -424,6 +428,14 @@ static int nvrtc_build(const char* const* srcs, int nsrc, const char* logfn_name
         opts.push_back("-DBAY_MIRROR=1");
         opts.push_back("-DBAY_DIMA=" + std::to_string((dim + 3) / 4 * 4));
     }
+    // Occupancy floor: a thread holds the whole proposal (DIM floats), so for large DIM ptxas takes 255 registers
+    // and only 8 warps fit an SM — the kernel then stalls on load latency (ncu: long_scoreboard).  Asking for more
+    // resident CTAs caps the registers and trades L1-resident spills for more warps.  BAY_MINB overrides.
+    {
+        int minb = 1;   // measured on DIM = 100: 1 and 8 tie (0.86 ms), 4 is worse (L1 thrash by local arrays)
+        if (const char* env = getenv("BAY_MINB")) minb = atoi(env);
+        if (minb > 1) opts.push_back("-DBAY_MINB=" + std::to_string(minb));
+    }
     if (verbose) opts.push_back("--ptxas-options=-v");
     std::vector<const char*> copts;
     for (auto& o : opts) copts.push_back(o.c_str());
@@ -490,7 +502,8 @@ extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsr
         return cu_fail(cr, "cuModuleLoadData");
     }
     struct { const char* name; CUfunction* f; } fns[] = {
-        {"bay_stretch_bare", &m->f_bare}, {"bay_stretch_accu", &m->f_accu}, {"bay_logfn", &m->f_logfn}};
+        {"bay_stretch_bare", &m->f_bare}, {"bay_stretch_accu", &m->f_accu}, {"bay_logfn", &m->f_logfn},
+        {"bay_stretch_loop", &m->f_loop}};
     for (auto& fn : fns) {
         cr = g_cu.ModuleGetFunction(fn.f, m->mod, fn.name);
         if (cr != CUDA_SUCCESS) {
@@ -498,6 +511,11 @@ extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsr
             delete m;
             return cu_fail(cr, fn.name);
         }
+    }
+    {
+        int per_sm = 0;
+        if (g_cu.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, m->f_loop, m->block, 0) == CUDA_SUCCESS)
+            m->loop_capacity = per_sm * e->sm_count;
     }
     if ((flags & BAY_MODEL_GLM_LOGISTIC) && dim % 4 == 0) {
         struct { const char* name; CUfunction* f; } gfns[] = {
@@ -561,6 +579,8 @@ static int sampler_alloc(bay_sampler* s) {
     const size_t W = (size_t)s->W, D = (size_t)s->D, wgs = (size_t)e->wgs;
     CK(cudaMalloc(&s->xs, sizeof(float) * D * W));
     CK(cudaMalloc(&s->lp, sizeof(float) * W));
+    CK(cudaMalloc(&s->loop_bar, sizeof(unsigned int) * 2));
+    CK(cudaMemsetAsync(s->loop_bar, 0, sizeof(unsigned int) * 2, e->stream));
     if (s->m->mirror) {
         CK(cudaMalloc(&s->xa, sizeof(float) * W * (size_t)s->m->dima));
         CK(cudaMemsetAsync(s->xa, 0, sizeof(float) * W * (size_t)s->m->dima, e->stream));
@@ -652,7 +672,7 @@ extern "C" int bay_sampler_release(bay_sampler* s) {
     if (s->own_params) cudaFree(s->params);
     glm_release(s);
     void* bufs[] = {s->xs, s->lp, s->accept, s->blk_sums, s->accept_total, s->means, s->hist_counts, s->mm,
-                    s->limits, s->pdf, s->ranks, s->macc, s->vec_d, s->stage, s->xa};
+                    s->limits, s->pdf, s->ranks, s->macc, s->vec_d, s->stage, s->xa, s->loop_bar, s->loop_betas};
     for (void* b : bufs) if (b) cudaFree(b);
     delete s;
     return BAY_OK;
@@ -749,10 +769,54 @@ static int half_accu(bay_sampler* s, int half, uint32_t seed, uint32_t tag, floa
     return launch(m->e, m->f_accu, s->G, m->e->wgs, args);
 }
 
+// Persistent step loop (bay_stretch_loop): n moves in one cooperative launch when the whole half-ensemble is
+// co-resident — the launch-latency-bound regime of small ensembles.  BAY_LOOP=0 disables it.
+static bool loop_usable(const bay_sampler* s, int64_t n) {
+    const bay_model* m = s->m;
+    if (m->glm || !m->f_loop || n < 2) return false;
+    if ((int64_t)cdiv(s->H, m->block) > m->loop_capacity) return false;
+    static const int off = [] { const char* env = getenv("BAY_LOOP"); return (env && env[0] == '0') ? 1 : 0; }();
+    return !off;
+}
+
+static int move_bare_loop(bay_sampler* s, int64_t n, const float* betas, float cA, float cB, float cC) {
+    bay_model* m = s->m;
+    bay_engine* e = m->e;
+    float* betas_dev = nullptr;
+    if (betas) {
+        if (s->loop_betas_cap < n) {
+            if (s->loop_betas) { CK(cudaStreamSynchronize(e->stream)); CK(cudaFree(s->loop_betas)); s->loop_betas = nullptr; }
+            CK(cudaMalloc(&s->loop_betas, sizeof(float) * n));
+            s->loop_betas_cap = n;
+        }
+        CK(cudaMemcpyAsync(s->loop_betas, betas, sizeof(float) * n, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));   // betas is a caller-owned host vector
+        betas_dev = s->loop_betas;
+    }
+    int64_t done = 0;
+    while (done < n) {
+        const int64_t chunk = (n - done) < (1 << 20) ? (n - done) : (1 << 20);
+        uint32_t K = (uint32_t)s->H, pitch = (uint32_t)s->W, seed = (uint32_t)s->bare_seed, step0 = s->bare_counter;
+        uint32_t n_steps = (uint32_t)chunk;
+        float beta_const = s->beta;
+        const float* bptr = betas_dev ? betas_dev + done : nullptr;
+        void* args[] = {&K, &seed, &s->data_len, &s->params_len, &s->params, &s->xs, &pitch, &s->lp, &cA, &cB, &cC,
+                        &bptr, &beta_const, &step0, &n_steps, &s->loop_bar, &s->xa};   // xa only with BAY_MIRROR
+        CUresult cr = g_cu.LaunchCooperativeKernel(m->f_loop, cdiv(K, m->block), 1, 1, m->block, 1, 1, 0,
+                                                   reinterpret_cast<CUstream>(e->stream), args);
+        if (cr != CUDA_SUCCESS) return cu_fail(cr, "cuLaunchCooperativeKernel(bay_stretch_loop)");
+        g_launches++;
+        s->bare_counter += (uint32_t)chunk;
+        done += chunk;
+    }
+    return BAY_OK;
+}
+
 // move-bare! G/:358-364: odd = (X=s0, S=s1, seed, tag 3333), even = (X=s1, S=s0, seed+1, tag 4444)
 static int move_bare_n(bay_sampler* s, int64_t n, const float* betas /* nullable: use s->beta */) {
     float cA, cB, cC;
     stretch_coeffs(s->a_bare, &cA, &cB, &cC);
+    if (loop_usable(s, n)) return move_bare_loop(s, n, betas, cA, cB, cC);
     for (int64_t i = 0; i < n; i++) {
         const float beta = betas ? betas[i] : s->beta;
         TRY(half_bare(s, 0, (uint32_t)s->bare_seed, 3333u, cA, cB, cC, beta, s->bare_counter));

@@ -331,16 +331,18 @@ def mvn_model(d: int = 100) -> DeviceModel:
         }}
         const float4* U = (const float4*)&params[{d}];
         REAL acc = 0.0f;
-        for (uint32_t i = 0; i < {d}; i++) {{
-            REAL r0 = 0.0f, r1 = 0.0f;
-            for (uint32_t j = i / 4; j < {q}; j++) {{
-                const float4 u = U[i * {q} + j];
+        for (uint32_t b = 0; b < {q}; b++) {{      /* four rows of U at a time: each c[j] feeds 16 independent FMAs */
+            REAL r0 = 0.0f, r1 = 0.0f, r2 = 0.0f, r3 = 0.0f;
+            const float4* U0 = &U[(4 * b) * {q}];
+            for (uint32_t j = b; j < {q}; j++) {{
                 const float4 v = c[j];
-                r0 += u.x * v.x + u.y * v.y;
-                r1 += u.z * v.z + u.w * v.w;
+                const float4 u0 = U0[j], u1 = U0[{q} + j], u2 = U0[2 * {q} + j], u3 = U0[3 * {q} + j];
+                r0 += (u0.x * v.x + u0.y * v.y) + (u0.z * v.z + u0.w * v.w);
+                r1 += (u1.x * v.x + u1.y * v.y) + (u1.z * v.z + u1.w * v.w);
+                r2 += (u2.x * v.x + u2.y * v.y) + (u2.z * v.z + u2.w * v.w);
+                r3 += (u3.x * v.x + u3.y * v.y) + (u3.z * v.z + u3.w * v.w);
             }}
-            const REAL r = r0 + r1;
-            acc += r * r;
+            acc += (r0 * r0 + r1 * r1) + (r2 * r2 + r3 * r3);
         }}
         return -0.5f * acc;"""
     src = distribution_source(f"mvn{d}_mcmc_logpdf", body)
