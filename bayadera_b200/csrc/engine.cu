@@ -243,6 +243,7 @@ struct bay_model {
     CUmodule mod = nullptr;
     CUfunction f_bare = nullptr, f_accu = nullptr, f_logfn = nullptr, f_loop = nullptr;
     int loop_capacity = 0;   // co-resident CTAs of the persistent step-loop kernel on this device
+    int loop_block = 128;    // its CTA size
     // GLM (row-additive Bernoulli-logit) path, present iff `glm`
     CUfunction f_glm_propose = nullptr, f_glm_loglik = nullptr, f_glm_lp_init = nullptr, f_glm_accept = nullptr;
     bool glm = false;
@@ -402,6 +403,10 @@ static bool model_wants_mirror(int dim, uint32_t flags) {
     return !(env && env[0] == '0');
 }
 
+// CTA size of the persistent step-loop kernel: as large as the register budget of a DIM-float proposal allows,
+// so that few CTAs arrive at each grid barrier.
+static int loop_block_for(int dim, int block) { return dim <= 2 ? 1024 : (dim <= 8 ? 512 : block); }
+
 // NVRTC step shared by bay_model_compile and bay_model_compile_check.
 // gtx-stretch-factory (G/:747-757): model sources first, engine kernels after;
 // stretch-options (G/:630-633) retargeted to sm_100a.
@@ -436,6 +441,7 @@ static int nvrtc_build(const char* const* srcs, int nsrc, const char* logfn_name
         if (const char* env = getenv("BAY_MINB")) minb = atoi(env);
         if (minb > 1) opts.push_back("-DBAY_MINB=" + std::to_string(minb));
     }
+    opts.push_back("-DBAY_LOOP_BLOCK=" + std::to_string(loop_block_for(dim, block)));
     if (verbose) opts.push_back("--ptxas-options=-v");
     std::vector<const char*> copts;
     for (auto& o : opts) copts.push_back(o.c_str());
@@ -514,7 +520,8 @@ extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsr
     }
     {
         int per_sm = 0;
-        if (g_cu.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, m->f_loop, m->block, 0) == CUDA_SUCCESS)
+        m->loop_block = loop_block_for(dim, m->block);
+        if (g_cu.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, m->f_loop, m->loop_block, 0) == CUDA_SUCCESS)
             m->loop_capacity = per_sm * e->sm_count;
     }
     if ((flags & BAY_MODEL_GLM_LOGISTIC) && dim % 4 == 0) {
@@ -774,7 +781,7 @@ static int half_accu(bay_sampler* s, int half, uint32_t seed, uint32_t tag, floa
 static bool loop_usable(const bay_sampler* s, int64_t n) {
     const bay_model* m = s->m;
     if (m->glm || !m->f_loop || n < 2) return false;
-    if ((int64_t)cdiv(s->H, m->block) > m->loop_capacity) return false;
+    if ((int64_t)cdiv(s->H, m->loop_block) > m->loop_capacity) return false;
     static const int off = [] { const char* env = getenv("BAY_LOOP"); return (env && env[0] == '0') ? 1 : 0; }();
     return !off;
 }
@@ -802,7 +809,7 @@ static int move_bare_loop(bay_sampler* s, int64_t n, const float* betas, float c
         const float* bptr = betas_dev ? betas_dev + done : nullptr;
         void* args[] = {&K, &seed, &s->data_len, &s->params_len, &s->params, &s->xs, &pitch, &s->lp, &cA, &cB, &cC,
                         &bptr, &beta_const, &step0, &n_steps, &s->loop_bar, &s->xa};   // xa only with BAY_MIRROR
-        CUresult cr = g_cu.LaunchCooperativeKernel(m->f_loop, cdiv(K, m->block), 1, 1, m->block, 1, 1, 0,
+        CUresult cr = g_cu.LaunchCooperativeKernel(m->f_loop, cdiv(K, m->loop_block), 1, 1, m->loop_block, 1, 1, 0,
                                                    reinterpret_cast<CUstream>(e->stream), args);
         if (cr != CUDA_SUCCESS) return cu_fail(cr, "cuLaunchCooperativeKernel(bay_stretch_loop)");
         g_launches++;
