@@ -269,6 +269,7 @@ struct bay_sampler {
     float* loop_betas = nullptr;        // per-step inverse temperatures (anneal!)
     int64_t loop_betas_cap = 0;
     uint32_t* accept = nullptr;               // G
+    uint32_t* accept_all = nullptr;           // G: all-reduced copy (walker-partitioned multi-GPU)
     float* blk_sums = nullptr;                // D x G
     unsigned long long* accept_total = nullptr;  // 1
     float* means = nullptr;                   // D x means_cap
@@ -618,6 +619,9 @@ static int sampler_create_common(bay_model* m, int32_t seed, int64_t walkers, in
     if (walkers < 2 * wgs || walkers % (2 * wgs) != 0 || walkers > (int64_t)1 << 31)
         return fail(BAY_EINVAL_WALKERS, "Number of walkers (%lld) must be a multiple of %d.", (long long)walkers, 2 * wgs);
     if (params_count < 0) return fail(BAY_EINVAL, "negative params_count");
+    if (m->e->comm && m->e->nranks > 1 && !m->glm && walkers % ((int64_t)2 * wgs * m->e->nranks) != 0)
+        return fail(BAY_EINVAL_WALKERS, "Number of walkers (%lld) must be a multiple of %d.", (long long)walkers,
+                    2 * wgs * m->e->nranks);
     TRY(use_device(m->e));
     bay_sampler* s = new bay_sampler();
     s->m = m;
@@ -679,7 +683,7 @@ extern "C" int bay_sampler_release(bay_sampler* s) {
     if (s->own_params) cudaFree(s->params);
     glm_release(s);
     void* bufs[] = {s->xs, s->lp, s->accept, s->blk_sums, s->accept_total, s->means, s->hist_counts, s->mm,
-                    s->limits, s->pdf, s->ranks, s->macc, s->vec_d, s->stage, s->xa, s->loop_bar, s->loop_betas};
+                    s->limits, s->pdf, s->ranks, s->macc, s->vec_d, s->stage, s->xa, s->loop_bar, s->loop_betas, s->accept_all};
     for (void* b : bufs) if (b) cudaFree(b);
     delete s;
     return BAY_OK;
@@ -746,6 +750,40 @@ extern "C" int bay_init_position_from(bay_sampler* s, const bay_sampler* other) 
     return BAY_OK;
 }
 
+// ---- multi-GPU mode A: walker partition ------------------------------------------------------
+// With a communicator, a non-GLM sampler's ensemble is replicated on every rank but rank r only UPDATES the walkers
+// [r*H/R, (r+1)*H/R) of the active half; the updated slice (SoA rows, log-densities, mirror rows) is then
+// all-gathered so that every rank holds the full half for the next half-step's partner gather.  Philox counters
+// are global walker indices and every walker is computed by the same code from the same inputs, so an R-GPU chain
+// is bit-identical to the 1-GPU chain.
+static bool partitioned(const bay_sampler* s) { return s->m->e->comm != nullptr && s->m->e->nranks > 1 && !s->m->glm; }
+
+static void my_slice(const bay_sampler* s, uint32_t* k_begin, uint32_t* k_end) {
+    if (!partitioned(s)) { *k_begin = 0; *k_end = (uint32_t)s->H; return; }
+    const uint32_t hs = (uint32_t)(s->H / s->m->e->nranks);
+    *k_begin = hs * (uint32_t)s->m->e->rank;
+    *k_end = *k_begin + hs;
+}
+
+static int exchange_half(bay_sampler* s, int half) {
+    if (!partitioned(s)) return BAY_OK;
+    bay_engine* e = s->m->e;
+    const size_t hs = (size_t)(s->H / e->nranks), H = (size_t)s->H, W = (size_t)s->W, r = (size_t)e->rank;
+    const size_t h0 = half ? H : 0;
+    CKNCCL(g_nccl.GroupStart());
+    for (int d = 0; d < s->D; d++) {
+        float* row = s->xs + (size_t)d * W + h0;
+        CKNCCL(g_nccl.AllGather(row + r * hs, row, hs, ncclFloat, e->comm, e->stream));
+    }
+    CKNCCL(g_nccl.AllGather(s->lp + h0 + r * hs, s->lp + h0, hs, ncclFloat, e->comm, e->stream));
+    if (s->xa) {
+        float* base = s->xa + h0 * s->m->dima;
+        CKNCCL(g_nccl.AllGather(base + r * hs * s->m->dima, base, hs * s->m->dima, ncclFloat, e->comm, e->stream));
+    }
+    CKNCCL(g_nccl.GroupEnd());
+    return BAY_OK;
+}
+
 static int half_bare(bay_sampler* s, int half, uint32_t seed, uint32_t tag, float cA, float cB, float cC,
                      float beta, uint32_t step) {
     bay_model* m = s->m;
@@ -756,9 +794,12 @@ static int half_bare(bay_sampler* s, int half, uint32_t seed, uint32_t tag, floa
     float* lp = s->lp + (half ? s->H : 0);
     float* cmp_a = s->xa ? s->xa + (size_t)(half ? 0 : s->H) * m->dima : nullptr;
     float* act_a = s->xa ? s->xa + (size_t)(half ? s->H : 0) * m->dima : nullptr;
+    uint32_t kb, ke;
+    my_slice(s, &kb, &ke);
     void* args[] = {&K, &seed, &tag, &s->data_len, &s->params_len, &s->params, &cmp, &act, &pitch, &lp,
-                    &cA, &cB, &cC, &beta, &step, &cmp_a, &act_a};   // the last two only exist with BAY_MIRROR
-    return launch(m->e, m->f_bare, cdiv(K, m->block), m->block, args);
+                    &cA, &cB, &cC, &beta, &step, &kb, &ke, &cmp_a, &act_a};   // the last two only exist with BAY_MIRROR
+    TRY(launch(m->e, m->f_bare, cdiv(ke - kb, m->block), m->block, args));
+    return exchange_half(s, half);
 }
 
 static int half_accu(bay_sampler* s, int half, uint32_t seed, uint32_t tag, float cA, float cB, float cC,
@@ -771,16 +812,19 @@ static int half_accu(bay_sampler* s, int half, uint32_t seed, uint32_t tag, floa
     float* lp = s->lp + (half ? s->H : 0);
     float* cmp_a = s->xa ? s->xa + (size_t)(half ? 0 : s->H) * m->dima : nullptr;
     float* act_a = s->xa ? s->xa + (size_t)(half ? s->H : 0) * m->dima : nullptr;
+    uint32_t kb, ke;
+    my_slice(s, &kb, &ke);
     void* args[] = {&K, &seed, &tag, &s->data_len, &s->params_len, &s->params, &cmp, &act, &pitch, &lp,
-                    &s->accept, &s->blk_sums, &cA, &cB, &cC, &step, &accumulate, &cmp_a, &act_a};
-    return launch(m->e, m->f_accu, s->G, m->e->wgs, args);
+                    &s->accept, &s->blk_sums, &cA, &cB, &cC, &step, &accumulate, &kb, &ke, &cmp_a, &act_a};
+    TRY(launch(m->e, m->f_accu, cdiv(ke - kb, m->e->wgs), m->e->wgs, args));
+    return exchange_half(s, half);
 }
 
 // Persistent step loop (bay_stretch_loop): n moves in one cooperative launch when the whole half-ensemble is
 // co-resident — the launch-latency-bound regime of small ensembles.  BAY_LOOP=0 disables it.
 static bool loop_usable(const bay_sampler* s, int64_t n) {
     const bay_model* m = s->m;
-    if (m->glm || !m->f_loop || n < 2) return false;
+    if (m->glm || !m->f_loop || n < 2 || partitioned(s)) return false;
     if ((int64_t)cdiv(s->H, m->loop_block) > m->loop_capacity) return false;
     static const int off = [] { const char* env = getenv("BAY_LOOP"); return (env && env[0] == '0') ? 1 : 0; }();
     return !off;
@@ -926,8 +970,12 @@ extern "C" int bay_move(bay_sampler* s) {
     float cA, cB, cC;
     stretch_coeffs(s->a_move, &cA, &cB, &cC);
     TRY(ensure_means(s, s->means_n + 1));
+    if (partitioned(s))   // blocks of other ranks must contribute exact zeros to the all-reduce below
+        CK(cudaMemsetAsync(s->blk_sums, 0, sizeof(float) * (size_t)s->D * s->G, e->stream));
     TRY(half_accu(s, 0, (uint32_t)s->move_seed, 1111u, cA, cB, cC, s->move_counter));
     TRY(half_accu(s, 1, (uint32_t)(s->move_seed + 1), 2222u, cA, cB, cC, s->move_counter));
+    if (partitioned(s))   // every block sum is produced by exactly one rank: x + 0 + ... + 0 is exact
+        CKNCCL(g_nccl.AllReduce(s->blk_sums, s->blk_sums, (size_t)s->D * s->G, ncclFloat, ncclSum, e->comm, e->stream));
     const float factor = 0.5f / ((float)e->wgs * (float)s->G);
     bay::k_step_means<<<cdiv((uint64_t)s->D * 32, 128), 128, 0, e->stream>>>(
         (uint32_t)s->D, s->G, s->blk_sums, factor, s->means + (size_t)s->means_n * s->D);
