@@ -242,10 +242,13 @@ def main():
     assert stream.cuda_stream != 0
     factory = bb.B200BayaderaFactory(device=local_rank, stream=stream.cuda_stream, wgs=args.wgs)
     assert factory.stream() == stream.cuda_stream
-    sharded = bool(wl.get("glm")) and world > 1
-    if sharded:
-        # SURVEY §8e mode B: walkers replicated, dataset rows sharded, per-walker partial sums all-reduced by the
-        # engine over NCCL.  Total work is fixed (10^7 rows) -> strong scaling.
+    sharded = bool(wl.get("glm")) and world > 1          # SURVEY §8e mode B
+    partition = (not wl.get("glm")) and world > 1        # SURVEY §8e mode A
+    if world > 1:
+        # mode B (GLM): walkers replicated, dataset rows sharded, per-walker partial sums all-reduced by the engine
+        #   over NCCL; total work fixed (10^7 rows) -> strong scaling.
+        # mode A (generic models): ONE global ensemble of world*W walkers, rank r updates its slice of each half and
+        #   the slices are all-gathered every half-step; per-GPU walkers fixed -> weak scaling.
         from bayadera_b200.distributed import init_engine_comm, shard_rows
         init_engine_comm(factory, rank, world, torch.device("cuda", local_rank))
     sfactory = factory.mcmc_factory(model)
@@ -257,10 +260,10 @@ def main():
         else:
             local_rows, seed = wl["rows"], 2024
         params = bb.DeviceParams.from_torch(logreg_rows_device(torch, local_rows, D, seed, torch.device("cuda", local_rank)))
-    # replicated walkers need identical seeds on every rank; independent replicas (non-GLM, N>1) differ by rank
-    seed_off = 0 if sharded else rank
-    sampler = sfactory.create_sampler(123 + seed_off, W, params)
-    sampler.init_position(1000 + seed_off, wl["limits"])
+    # every rank drives the same (replicated or partitioned) ensemble: identical seeds everywhere
+    W_global = W * world if partition else W
+    sampler = sfactory.create_sampler(123, W_global, params)
+    sampler.init_position(1000, wl["limits"])
     sampler.burn_in(max(64, M), a)                      # leave the initial box before timing
     p_acc = sampler.acc_rate(a)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -359,7 +362,9 @@ def main():
                            "acceptance": round(p_acc, 4), "wgs": args.wgs,
                            "parallelism": "single GPU" if world == 1 else (
                                f"rows sharded over {world} GPUs, walkers replicated, NCCL all-reduce of per-walker sums"
-                               if sharded else f"{world} independent replicas (no exchange)"),
+                               if sharded else
+                               f"one ensemble of {W_global} walkers partitioned over {world} GPUs, NCCL all-gather of the "
+                               "updated slice every half-step"),
                            "l2": "flushed between timed steps (256 MiB write)",
                            "kernel": {"name": kernel_name, **info}},
                 "e2e": {"value": e2e_value, "unit": UNIT,

@@ -62,12 +62,12 @@ def main():
         sa, sb = a.get_state(), b.get_state()
         assert np.array_equal(sa["xs"], sb["xs"]), f"{name}: positions differ from the 1-GPU chain"
         assert np.array_equal(sa["logfn"], sb["logfn"], equal_nan=True), f"{name}: log-densities differ"
-        ra, rb = a.run_sampler(12, 2.0), b.run_sampler(12, 2.0)
+        ra, rb = a.run_sampler(64, 2.0), b.run_sampler(64, 2.0)
         assert ra["acceptance-rate"] == rb["acceptance-rate"], name
         acc_a, sums_a = a.accu_blocks()
         acc_b, sums_b = b.accu_blocks()
         assert np.array_equal(acc_a, acc_b) and np.array_equal(sums_a, sums_b), name
-        assert np.array_equal(a.last_means(12), b.last_means(12)), name
+        assert np.array_equal(a.last_means(64), b.last_means(64)), name
         assert np.array_equal(ra["autocorrelation"].tau, rb["autocorrelation"].tau, equal_nan=True), name
         ha, hb = a.histogram(3), b.histogram(3)
         assert np.array_equal(a.histogram_counts(), b.histogram_counts()), name
@@ -101,7 +101,8 @@ def main():
     xs_s, lp_s = sharded.get_state64()
     xs_w, lp_w = whole.get_state64()
     assert np.array_equal(xs_s, xs_w)
-    assert np.allclose(lp_s, lp_w, rtol=1e-9), np.abs(lp_s / lp_w - 1).max()
+    # sharding changes which CTA sums which tiles (fp32 partial sums regroup): agreement to ~1e-8, bound 1e-7
+    assert np.allclose(lp_s, lp_w, rtol=1e-7), np.abs(lp_s / lp_w - 1).max()
     assert all_equal_across_ranks(lp_s), "all-reduced log-densities must be bit-identical on every rank"
     for s in (sharded, whole):
         s.burn_in(4, 1.5)
@@ -110,7 +111,7 @@ def main():
     same = np.all(xs_s == xs_w, axis=1)
     assert same.mean() > 0.995, same.mean()
     assert all_equal_across_ranks(xs_s) and all_equal_across_ranks(lp_s), "replicas diverged"
-    r = sharded.run_sampler(8, 1.5)
+    r = sharded.run_sampler(64, 1.5)
     assert 0.0 < r["acceptance-rate"] < 1.0
 
     dist.barrier()
