@@ -8,9 +8,11 @@ from . import mcmc, models
 from ._lib import (AcorTooShortError, BayaderaError, ModelCompileError, WalkerCountError, LIB_PATH)
 from .engine import (Autocorrelation, B200AcorEngine, DeviceParams, B200BayaderaFactory, B200DatasetEngine, B200Stretch,
                      B200StretchFactory, Histogram, launch_count, nccl_unique_id)
+from .engines import B200DirectSamplerEngine, B200DistributionEngine, B200LikelihoodEngine
 from .models import DeviceModel
 
 __all__ = ["mcmc", "models", "DeviceModel", "B200BayaderaFactory", "B200StretchFactory", "B200Stretch",
-           "B200DatasetEngine", "B200AcorEngine", "DeviceParams", "Histogram", "Autocorrelation", "BayaderaError",
+           "B200DatasetEngine", "B200AcorEngine", "DeviceParams", "B200DistributionEngine", "B200LikelihoodEngine",
+           "B200DirectSamplerEngine", "Histogram", "Autocorrelation", "BayaderaError",
            "WalkerCountError", "AcorTooShortError", "ModelCompileError", "launch_count", "nccl_unique_id",
            "LIB_PATH"]

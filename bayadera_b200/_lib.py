@@ -92,6 +92,9 @@ SIGNATURES = {
     "bay_dataset_histogram": (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "bay_acor": (C.c_int, [_vp, _f32, _i64, _i64, _vp, _vp, _vp, C.POINTER(_i64)]),
     "bay_model_logfn": (C.c_int, [_vp, _vp, _i64, _f32, _i64, _f32]),
+    "bay_model_density": (C.c_int, [_vp, _vp, _i64, _f32, _i64, C.c_int, _f32]),
+    "bay_model_evidence": (C.c_int, [_vp, _vp, _i64, _f32, _i64, C.POINTER(C.c_double)]),
+    "bay_direct_sample": (C.c_int, [_vp, C.c_int, _i32, _f32, C.c_int, _i64, _vp, C.c_int]),
     "bay_launch_count": (_i64, []),
 }
 

@@ -986,3 +986,6 @@ extern "C" int bay_move(bay_sampler* s) {
 }
 
 #include "engine_estimate.inc"
+
+#include "kernels_rng.cuh"
+#include "engine_next.inc"

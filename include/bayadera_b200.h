@@ -176,6 +176,19 @@ int bay_acor(bay_engine *e, const float *series_host, int64_t dim, int64_t n, fl
 int bay_model_logfn(bay_model *m, const float *params_host, int64_t params_count,
                     const float *x_host, int64_t n, float *out_host);
 
+/* ---- callers either side of the hot path ----
+ * DensityEngine.log-density / density (P/:75-77; G/:67-131): the model is compiled with logfn_name = its logpdf
+ * (distribution engine) or a loglik wrapper (likelihood engine, see bayadera_b200.models.likelihood_engine_model). */
+int bay_model_density(bay_model *m, const float *params_host, int64_t params_count, const float *x_host,
+                      int64_t n, int exponentiate, float *out_host);
+/* LikelihoodEngine.evidence (P/:79-80; G/:132-141): mean over the n points of exp(logfn), double accumulation */
+int bay_model_evidence(bay_model *m, const float *params_host, int64_t params_count, const float *x_host,
+                       int64_t n, double *out);
+/* RandomSamplerEngine.sample [seed params res] (P/:90-92; G/:48-63; K/rng/<family>-sampler.cu): family 0 uniform [a b],
+ * 1 gaussian [mu sigma], 2 exponential [lambda], 3 erlang [lambda k]; n a multiple of 4; out: 1 x n. */
+int bay_direct_sample(bay_engine *e, int family, int32_t seed, const float *params_host, int nparams, int64_t n,
+                      void *out, int out_is_device);
+
 /* profiling counters: kernels launched by this library on the calling process */
 int64_t bay_launch_count(void);
 

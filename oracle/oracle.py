@@ -34,8 +34,8 @@ _u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
 
 
 def build(force: bool = False) -> Path:
-    src = _HERE / "bayadera_oracle.c"
-    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+    newest = max((_HERE / f).stat().st_mtime for f in ("bayadera_oracle.c", "bayadera_oracle_rng.c"))
+    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < newest:
         subprocess.run(["make", "-C", str(_HERE), "-B"], check=True, capture_output=True)
     return _LIB_PATH
 

@@ -30,6 +30,23 @@ DIRECT_UNIFORM = dict(
     last4=(17.43636131286621, 151.42117309570312, 42.78262710571289, 107.87583923339844),
     max=200.0757293701172, min=-99.86572265625, mean=51.331178125)
 
+# the other direct samplers, seed 123, n = 10000 (nvidia_gtx_test.clj:56-107); compiled with -use_fast_math in the
+# reference, so they embed MUFU approximations: pinned with a relative tolerance, not bit-for-bit
+DIRECT = {
+    "gaussian": dict(params=(100, 200.1),
+                     first4=(-27.02083969116211, 55.2710075378418, 185.74417114257812, 322.7049255371094),
+                     last4=(175.25135803222656, 7.720771312713623, 126.18173217773438, -69.4984359741211),
+                     max=868.6444702148438, min=-610.0802612304688, mean=95.13473125),
+    "erlang": dict(params=(2, 3),
+                   first4=(1.571028470993042, 1.4484456777572632, 0.798355758190155, 1.1712464094161987),
+                   last4=(0.7548800110816956, 2.2858035564422607, 1.19755220413208, 1.3439300060272217),
+                   max=7.1595940589904785, min=0.04825383424758911, mean=1.5008442260742187),
+    "exponential": dict(params=(4,),
+                        first4=(0.29777514934539795, 0.3990693986415863, 0.015068254433572292, 0.1688637137413025),
+                        last4=(0.12403398752212524, 0.45463457703590393, 0.16137929260730743, 0.29489004611968994),
+                        max=2.3556251525878906, min=2.8555818062159233E-5, mean=0.25263106842041017),
+}
+
 # Uniform(-1,2) stretch, limits [-1 2]: xs[0..3] after each of 4 sample! calls (nvidia_gtx_test.clj:200-212)
 UNIFORM_SAMPLES = [
     (0.7279692888259888, 1.81407630443573, 0.040318019688129425, 0.4697103202342987),

@@ -157,3 +157,16 @@ def test_histogram_pipeline_properties():
 def test_walker_count_check():
     with pytest.raises(ValueError, match="must be a multiple of 512"):
         orc.OracleStretch(models.GAUSSIAN, 1, 300, f32([0, 1]), wgs=256)
+
+
+@pytest.mark.parametrize("family", ["gaussian", "erlang", "exponential"])
+def test_direct_sampler_goldens_within_fast_math_tolerance(family):
+    """nvidia_gtx_test.clj:56-107.  The reference builds these kernels with -use_fast_math; libm agrees to ~4e-6."""
+    from oracle import oracle_rng
+    g = G.DIRECT[family]
+    x = oracle_rng.direct_sample(family, 10000, G.SEED, g["params"])
+    assert np.allclose(x[:4], f32(g["first4"]), rtol=2e-5)
+    assert np.allclose(x[-4:], f32(g["last4"]), rtol=2e-5)
+    assert abs(float(x.max()) / g["max"] - 1) < 2e-5
+    assert abs(float(x.min()) / g["min"] - 1) < 1e-3        # log(1-u) at u ~ 1e-4: lg2 approximation shows
+    assert abs(float(x.astype(np.float64).mean()) / g["mean"] - 1) < 1e-5
