@@ -161,8 +161,14 @@ __global__ void k_minmax_decode(uint32_t dim, const uint32_t* __restrict__ mm, f
 // -------------------------------------------------------------- histogram --
 // histogram (estimate.cu:5-32).  bin = clamp(floor(((x-lo)/(hi-lo))*BINS), 0, BINS-1)
 // in IEEE fp32 — integer counts, bit-exact against the oracle.
+// Fast path: t' = (x-lo) * (BINS/range) differs from the defining expression by a few ulp, so floor(t') is the
+// defining bin unless t' sits within 1e-6 relative of an integer; only then (and for NaN / out-of-range values)
+// is the IEEE division evaluated.  The counts stay bit-exact while the common case costs a multiply.
 __device__ __forceinline__ uint32_t hist_bin(float x, float lo, float range, float fbins, uint32_t bins) {
-    const float t = __fmul_rn(__fdiv_rn(__fsub_rn(x, lo), range), fbins);
+    const float d = __fsub_rn(x, lo);
+    const float ta = d * __fdividef(fbins, range);
+    if (ta > 0.5f && ta < fbins - 0.5f && fabsf(ta - rintf(ta)) > 1e-6f * (ta + 1.0f)) return (uint32_t)ta;
+    const float t = __fmul_rn(__fdiv_rn(d, range), fbins);
     uint32_t b;
     if (!(t > 0.0f)) b = 0;
     else if (t >= fbins) b = bins - 1;

@@ -191,6 +191,43 @@ def run_reference(args, wl: dict, rank: int, world: int):
     print(json.dumps(line), flush=True)
 
 
+# -------------------------------------------------------------------------------------------- summary --
+def run_summary(args):
+    """Not a bench line of record: device time of the summary engines on the config-5
+    ensemble (100 x 2^20 fp32 = 419 MB, larger than L2): histogram = min/max pass + binning pass + finish,
+    mean and variance = one fused pass each call.  Reported as GB/s of algorithmic bytes (4*D*n per pass)."""
+    import torch
+
+    import bayadera_b200 as bb
+    from bayadera_b200 import models
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    m = models.mvn_model(100)
+    factory = bb.B200BayaderaFactory(device=0, stream=stream.cuda_stream, wgs=args.wgs)
+    s = factory.mcmc_factory(m).create_sampler(1, 2 ** 20, models.mvn_params(100)[0]).init_position(2, m.limits_array())
+    nbytes = 4.0 * 100 * 2 ** 20
+    out = {}
+    for name, fn, passes in (("histogram (min/max + bin)", lambda: s.histogram(1), 2), ("mean", s.mean, 1),
+                             ("variance", s.variance, 1)):
+        for _ in range(3):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(args.steps):
+            fn()
+        b.record(stream)
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / args.steps
+        out[name] = {"ms_per_call": ms, "algorithmic_GBps": passes * nbytes / (ms * 1e-3) / 1e9, "passes": passes}
+    ds = factory.dataset_engine()
+    data = np.random.default_rng(0).random((31 * 2 ** 16, 22), dtype=np.float32)       # T/core_test.clj:19
+    t0 = time.perf_counter()
+    ds.histogram(data)
+    out["dataset histogram 22 x 2031616 from host (e2e)"] = {"ms_per_call": 1e3 * (time.perf_counter() - t0)}
+    print(json.dumps({"workload": "summary engines on the c5 ensemble (100 x 2^20)", "wgs": args.wgs, "results": out}))
+
+
 # ----------------------------------------------------------------------------------------------- main --
 def main():
     ap = argparse.ArgumentParser()
@@ -209,6 +246,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload == "summary":
+        run_summary(args)
+        return
     wl = workload(args.workload)
     if args.walkers:
         wl["walkers"] = args.walkers
