@@ -248,6 +248,7 @@ struct bay_model {
     CUfunction f_glm_propose = nullptr, f_glm_loglik = nullptr, f_glm_lp_init = nullptr, f_glm_accept = nullptr;
     bool glm = false;
     bool mirror = false;   // AoS mirror of the ensemble for the partner gather (DIM >= 4, non-GLM)
+    bool peers = false;    // kernels store accepted walkers into every rank's ensemble block (multi-GPU mode A)
     int dima = 1;          // mirror row length: DIM rounded up to a multiple of 4
     int dim = 1, params_size = 0;
     uint32_t flags = 0;
@@ -266,6 +267,13 @@ struct bay_sampler {
     float* lp = nullptr;  // W
     float* xa = nullptr;  // W x dima AoS mirror (only if m->mirror)
     unsigned int* loop_bar = nullptr;   // grid-barrier words of the persistent step loop
+    // multi-GPU mode A over peer memory: xs | lp | xa | flags live in ONE block that every rank maps (CUDA IPC)
+    float* peer_block = nullptr;
+    bay::PeerTable peer_tab;            // block base on every rank + offsets; passed by value to the kernels
+    uint64_t peer_flags_off = 0;        // offset (in 4-byte words) of the barrier flags inside the block
+    uint32_t peer_epoch = 0;
+    bool soa_stale = false;             // peers forwarded mirror rows only: rebuild xs from xa before a read-out
+    void* peer_mapped[8] = {nullptr};   // what cudaIpcOpenMemHandle returned (to close on release)
     float* loop_betas = nullptr;        // per-step inverse temperatures (anneal!)
     int64_t loop_betas_cap = 0;
     uint32_t* accept = nullptr;               // G
@@ -395,6 +403,14 @@ extern "C" int bay_engine_comm_init(bay_engine* e, const uint8_t id[128], int nr
 }
 
 // ------------------------------------------------------------------- model --
+// Walker-partitioned samplers exchange through peer memory (NVLink stores from the stretch kernel itself) unless
+// BAY_P2P=0 asks for the NCCL all-gather exchange instead (the baseline the peer path is measured against).
+static bool engine_wants_peers(const bay_engine* e) {
+    if (!e->comm || e->nranks < 2 || e->nranks > 8) return false;
+    const char* env = getenv("BAY_P2P");
+    return !(env && env[0] == '0');
+}
+
 // The AoS mirror pays off once a walker spans several 32-byte sectors; GLM models gather only H rows per half-step.
 // BAY_MIRROR=0 in the environment disables it (A/B measurements).
 static bool model_wants_mirror(int dim, uint32_t flags) {
@@ -412,7 +428,7 @@ static int loop_block_for(int dim, int block) { return dim <= 2 ? 1024 : (dim <=
 // gtx-stretch-factory (G/:747-757): model sources first, engine kernels after;
 // stretch-options (G/:630-633) retargeted to sm_100a.
 static int nvrtc_build(const char* const* srcs, int nsrc, const char* logfn_name, int dim, int wgs, int block,
-                       uint32_t flags, bool verbose, std::vector<char>* cubin, std::string* log_out) {
+                       uint32_t flags, bool peers, bool verbose, std::vector<char>* cubin, std::string* log_out) {
     if (!srcs || !logfn_name) return fail(BAY_EINVAL, "NULL argument");
     if (dim < 1 || dim > 4096) return fail(BAY_EINVAL, "dimension %d out of range", dim);
     if (wgs < 32 || wgs > 1024 || (wgs & (wgs - 1))) return fail(BAY_EINVAL, "wgs must be a power of two in [32, 1024], got %d", wgs);
@@ -434,6 +450,7 @@ static int nvrtc_build(const char* const* srcs, int nsrc, const char* logfn_name
         opts.push_back("-DBAY_MIRROR=1");
         opts.push_back("-DBAY_DIMA=" + std::to_string((dim + 3) / 4 * 4));
     }
+    if (peers) opts.push_back("-DBAY_PEERS=1");
     // Occupancy floor: a thread holds the whole proposal (DIM floats), so for large DIM ptxas takes 255 registers
     // and only 8 warps fit an SM — the kernel then stalls on load latency (ncu: long_scoreboard).  Asking for more
     // resident CTAs caps the registers and trades L1-resident spills for more warps.  BAY_MINB overrides.
@@ -477,7 +494,7 @@ extern "C" int bay_model_compile_check(const char* const* srcs, int nsrc, const 
                                        uint32_t flags, int64_t* cubin_bytes, char* log_buf, int64_t log_cap) {
     std::vector<char> cubin;
     std::string log;
-    int r = nvrtc_build(srcs, nsrc, logfn_name, dim, wgs, bare_block_for(dim), flags, true, &cubin, &log);
+    int r = nvrtc_build(srcs, nsrc, logfn_name, dim, wgs, bare_block_for(dim), flags, false, true, &cubin, &log);
     if (log_buf && log_cap > 0) {
         const std::string& text = r == BAY_OK ? log : g_err;
         snprintf(log_buf, (size_t)log_cap, "%s", text.c_str());
@@ -492,7 +509,9 @@ extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsr
     TRY(use_device(e));
     TRY(load_driver());
     std::vector<char> cubin;
-    TRY(nvrtc_build(srcs, nsrc, logfn_name, dim, e->wgs, bare_block_for(dim), flags, false, &cubin, nullptr));
+    const bool glm_model = (flags & BAY_MODEL_GLM_LOGISTIC) && dim % 4 == 0;
+    const bool peers = engine_wants_peers(e) && !glm_model;
+    TRY(nvrtc_build(srcs, nsrc, logfn_name, dim, e->wgs, bare_block_for(dim), flags, peers, false, &cubin, nullptr));
 
     bay_model* m = new bay_model();
     m->e = e;
@@ -501,6 +520,7 @@ extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsr
     m->flags = flags;
     m->block = bare_block_for(dim);
     m->mirror = model_wants_mirror(dim, flags);
+    m->peers = peers;
     m->dima = (dim + 3) / 4 * 4;
 
     CUresult cr = g_cu.ModuleLoadData(&m->mod, cubin.data());
@@ -582,17 +602,96 @@ static void stretch_coeffs(float a, float* cA, float* cB, float* cC) {
 
 #include "engine_glm.inc"
 
+// ---- multi-GPU mode A over peer memory ----------------------------------------------------------------------
+// One block per sampler holds [xs D x W | lp W | mirror W x dima | 16 barrier flags]; its IPC handle is all-gathered
+// over the engine's NCCL communicator (the only bootstrap channel the C ABI has) and every peer's block is mapped
+// here.  Collective: all ranks create (and release) their partitioned samplers in the same order.
+static int peer_block_alloc(bay_sampler* s) {
+    bay_engine* e = s->m->e;
+    const size_t W = (size_t)s->W, D = (size_t)s->D, dima = s->m->mirror ? (size_t)s->m->dima : 0;
+    const size_t lp_off = D * W, xa_off = lp_off + W, flags_off = xa_off + W * dima;
+    const size_t words = flags_off + 16;
+    CK(cudaMalloc(&s->peer_block, sizeof(float) * words));
+    CK(cudaMemsetAsync(s->peer_block, 0, sizeof(float) * words, e->stream));
+    s->xs = s->peer_block;
+    s->lp = s->peer_block + lp_off;
+    s->xa = dima ? s->peer_block + xa_off : nullptr;
+    s->peer_flags_off = flags_off;
+
+    cudaIpcMemHandle_t mine;
+    CK(cudaIpcGetMemHandle(&mine, s->peer_block));
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    char* dev = nullptr;
+    CK(cudaMalloc(&dev, hb * e->nranks));
+    std::vector<cudaIpcMemHandle_t> all((size_t)e->nranks);
+    cudaError_t ce = cudaMemcpyAsync(dev + hb * e->rank, &mine, hb, cudaMemcpyHostToDevice, e->stream);
+    ncclResult_t nr = ncclSuccess;
+    if (ce == cudaSuccess) nr = g_nccl.AllGather(dev + hb * e->rank, dev, hb, ncclChar, e->comm, e->stream);
+    if (ce == cudaSuccess && nr == ncclSuccess)
+        ce = cudaMemcpyAsync(all.data(), dev, hb * e->nranks, cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);   // also: every rank's block is zeroed by now
+    cudaFree(dev);
+    if (nr != ncclSuccess) return fail(BAY_ENCCL, "handle exchange failed: %s", g_nccl.GetErrorString(nr));
+    if (ce != cudaSuccess) return fail(BAY_ECUDA, "handle exchange failed: %s", cudaGetErrorString(ce));
+
+    bay::PeerTable& t = s->peer_tab;
+    memset(&t, 0, sizeof(t));
+    t.n = (uint32_t)e->nranks;
+    t.self = (uint32_t)e->rank;
+    t.lp_off = lp_off;
+    t.xa_off = xa_off;
+    for (int r = 0; r < e->nranks; r++) {
+        if (r == e->rank) { t.base[r] = (unsigned long long)(uintptr_t)s->peer_block; continue; }
+        void* p = nullptr;
+        ce = cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess);
+        if (ce != cudaSuccess)
+            return fail(BAY_ECUDA, "cannot map the ensemble of rank %d (no NVLink/P2P path?): %s — set BAY_P2P=0 for the "
+                        "NCCL exchange", r, cudaGetErrorString(ce));
+        s->peer_mapped[r] = p;
+        t.base[r] = (unsigned long long)(uintptr_t)p;
+    }
+    return BAY_OK;
+}
+
+// tiny all-reduce used as a host-visible rendezvous of all ranks
+static int comm_rendezvous(bay_engine* e) {
+    int* flag = nullptr;
+    CK(cudaMalloc(&flag, sizeof(int)));
+    cudaError_t ce = cudaMemsetAsync(flag, 0, sizeof(int), e->stream);
+    ncclResult_t nr = ncclSuccess;
+    if (ce == cudaSuccess) nr = g_nccl.AllReduce(flag, flag, 1, ncclInt, ncclSum, e->comm, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    cudaFree(flag);
+    if (nr != ncclSuccess) return fail(BAY_ENCCL, "rendezvous failed: %s", g_nccl.GetErrorString(nr));
+    if (ce != cudaSuccess) return fail(BAY_ECUDA, "rendezvous failed: %s", cudaGetErrorString(ce));
+    return BAY_OK;
+}
+
+static void peer_block_release(bay_sampler* s) {
+    if (!s->peer_block) return;
+    bay_engine* e = s->m->e;
+    // every half-step ended with the flag barrier, so no peer store is in flight once the streams are drained
+    for (int r = 0; r < 8; r++)
+        if (s->peer_mapped[r]) cudaIpcCloseMemHandle(s->peer_mapped[r]);
+    comm_rendezvous(e);                       // every mapping of this block is closed before it is freed
+    cudaFree(s->peer_block);
+    s->peer_block = nullptr;
+    s->xs = s->lp = s->xa = nullptr;
+}
+
 static int sampler_alloc(bay_sampler* s) {
     const bay_engine* e = s->m->e;
     const size_t W = (size_t)s->W, D = (size_t)s->D, wgs = (size_t)e->wgs;
-    CK(cudaMalloc(&s->xs, sizeof(float) * D * W));
-    CK(cudaMalloc(&s->lp, sizeof(float) * W));
+    if (s->m->peers) {
+        TRY(peer_block_alloc(s));
+    } else {
+        CK(cudaMalloc(&s->xs, sizeof(float) * D * W));
+        CK(cudaMalloc(&s->lp, sizeof(float) * W));
+        if (s->m->mirror) CK(cudaMalloc(&s->xa, sizeof(float) * W * (size_t)s->m->dima));
+    }
+    if (s->xa) CK(cudaMemsetAsync(s->xa, 0, sizeof(float) * W * (size_t)s->m->dima, e->stream));
     CK(cudaMalloc(&s->loop_bar, sizeof(unsigned int) * 2));
     CK(cudaMemsetAsync(s->loop_bar, 0, sizeof(unsigned int) * 2, e->stream));
-    if (s->m->mirror) {
-        CK(cudaMalloc(&s->xa, sizeof(float) * W * (size_t)s->m->dima));
-        CK(cudaMemsetAsync(s->xa, 0, sizeof(float) * W * (size_t)s->m->dima, e->stream));
-    }
     CK(cudaMalloc(&s->accept, sizeof(uint32_t) * s->G));
     CK(cudaMalloc(&s->blk_sums, sizeof(float) * D * s->G));
     CK(cudaMalloc(&s->accept_total, sizeof(unsigned long long)));
@@ -682,6 +781,7 @@ extern "C" int bay_sampler_release(bay_sampler* s) {
     cudaStreamSynchronize(s->m->e->stream);
     if (s->own_params) cudaFree(s->params);
     glm_release(s);
+    peer_block_release(s);   // clears xs / lp / xa when they live in the shared block
     void* bufs[] = {s->xs, s->lp, s->accept, s->blk_sums, s->accept_total, s->means, s->hist_counts, s->mm,
                     s->limits, s->pdf, s->ranks, s->macc, s->vec_d, s->stage, s->xa, s->loop_bar, s->loop_betas, s->accept_all};
     for (void* b : bufs) if (b) cudaFree(b);
@@ -711,6 +811,11 @@ static int mirror_sync(bay_sampler* s) {
     return BAY_OK;
 }
 
+static int peer_settle(bay_sampler* s);
+static int soa_fresh(bay_sampler* s);
+static int aos_to_soa(bay_engine* e, const float* in, uint64_t offset, uint64_t ld, uint32_t dim, uint64_t n, float* out,
+                      uint64_t pitch);
+
 static int launch_logfn_all(bay_sampler* s) {
     bay_model* m = s->m;
     if (m->glm) return glm_logfn_all(s);
@@ -731,6 +836,7 @@ extern "C" int bay_init_position_uniform(bay_sampler* s, int32_t seed, const flo
     CKLAUNCH();
     TRY(mirror_sync(s));
     TRY(launch_logfn_all(s));
+    TRY(peer_settle(s));
     // limits_host may be pageable: the async copy above is staged before return, but be safe
     CK(cudaStreamSynchronize(e->stream));
     s->iterations = 0;
@@ -743,9 +849,12 @@ extern "C" int bay_init_position_from(bay_sampler* s, const bay_sampler* other) 
     if (s->W != other->W || s->D != other->D) return fail(BAY_EINVAL, "samplers differ in shape");
     bay_engine* e = s->m->e;
     TRY(use_device(e));
+    TRY(soa_fresh(const_cast<bay_sampler*>(other)));
     CK(cudaMemcpyAsync(s->xs, other->xs, sizeof(float) * (size_t)s->D * s->W, cudaMemcpyDeviceToDevice, e->stream));
+    TRY(peer_settle(const_cast<bay_sampler*>(other)));
     TRY(mirror_sync(s));
     TRY(launch_logfn_all(s));
+    TRY(peer_settle(s));
     s->iterations = 0;
     return BAY_OK;
 }
@@ -768,6 +877,15 @@ static void my_slice(const bay_sampler* s, uint32_t* k_begin, uint32_t* k_end) {
 static int exchange_half(bay_sampler* s, int half) {
     if (!partitioned(s)) return BAY_OK;
     bay_engine* e = s->m->e;
+    if (s->m->peers) {
+        // the kernel already stored the accepted walkers into every rank's block: only a barrier is left, so that
+        // no rank starts the next half-step before all stores into its block have landed
+        s->peer_epoch++;
+        bay::k_peer_barrier<<<1, 32, 0, e->stream>>>(s->peer_tab, s->peer_flags_off, (uint32_t)e->rank, s->peer_epoch);
+        g_launches++;
+        CK(cudaGetLastError());
+        return BAY_OK;
+    }
     const size_t hs = (size_t)(s->H / e->nranks), H = (size_t)s->H, W = (size_t)s->W, r = (size_t)e->rank;
     const size_t h0 = half ? H : 0;
     CKNCCL(g_nccl.GroupStart());
@@ -784,6 +902,24 @@ static int exchange_half(bay_sampler* s, int half) {
     return BAY_OK;
 }
 
+// The half-step barrier orders "my stores have landed" before "you go on"; it does not stop a fast rank from storing
+// step k+1 walkers into a slow rank that is still READING the whole ensemble (sample!, histogram!, mean, state
+// hand-off) or REWRITING it (init-position!).  Every such whole-ensemble access therefore ends with one more flag
+// barrier: peers pass it only after this rank's access has completed.  (Collective: all ranks make the same calls.)
+static int peer_settle(bay_sampler* s) {
+    if (!partitioned(s) || !s->m->peers) return BAY_OK;
+    return exchange_half(s, 0);
+}
+
+// Peers forward only mirror rows (stretch_program.inc, bay_forward_peers): before anything reads the SoA matrix
+// outside a rank's own slice (sample!, histogram!, mean, state hand-off) it is rebuilt from the mirror.
+static int soa_fresh(bay_sampler* s) {
+    if (!s->soa_stale) return BAY_OK;
+    TRY(aos_to_soa(s->m->e, s->xa, 0, (uint64_t)s->m->dima, (uint32_t)s->D, (uint64_t)s->W, s->xs, (uint64_t)s->W));
+    s->soa_stale = false;
+    return BAY_OK;
+}
+
 static int half_bare(bay_sampler* s, int half, uint32_t seed, uint32_t tag, float cA, float cB, float cC,
                      float beta, uint32_t step) {
     bay_model* m = s->m;
@@ -796,9 +932,12 @@ static int half_bare(bay_sampler* s, int half, uint32_t seed, uint32_t tag, floa
     float* act_a = s->xa ? s->xa + (size_t)(half ? s->H : 0) * m->dima : nullptr;
     uint32_t kb, ke;
     my_slice(s, &kb, &ke);
-    void* args[] = {&K, &seed, &tag, &s->data_len, &s->params_len, &s->params, &cmp, &act, &pitch, &lp,
-                    &cA, &cB, &cC, &beta, &step, &kb, &ke, &cmp_a, &act_a};   // the last two only exist with BAY_MIRROR
-    TRY(launch(m->e, m->f_bare, cdiv(ke - kb, m->block), m->block, args));
+    uint32_t col0 = half ? K : 0u;
+    std::vector<void*> args = {&K, &seed, &tag, &s->data_len, &s->params_len, &s->params, &cmp, &act, &pitch, &lp,
+                               &cA, &cB, &cC, &beta, &step, &kb, &ke};
+    if (m->mirror) { args.push_back(&cmp_a); args.push_back(&act_a); }
+    if (m->peers) { args.push_back(&s->peer_tab); args.push_back(&col0); s->soa_stale = m->mirror; }
+    TRY(launch(m->e, m->f_bare, cdiv(ke - kb, m->block), m->block, args.data()));
     return exchange_half(s, half);
 }
 
@@ -814,9 +953,12 @@ static int half_accu(bay_sampler* s, int half, uint32_t seed, uint32_t tag, floa
     float* act_a = s->xa ? s->xa + (size_t)(half ? s->H : 0) * m->dima : nullptr;
     uint32_t kb, ke;
     my_slice(s, &kb, &ke);
-    void* args[] = {&K, &seed, &tag, &s->data_len, &s->params_len, &s->params, &cmp, &act, &pitch, &lp,
-                    &s->accept, &s->blk_sums, &cA, &cB, &cC, &step, &accumulate, &kb, &ke, &cmp_a, &act_a};
-    TRY(launch(m->e, m->f_accu, cdiv(ke - kb, m->e->wgs), m->e->wgs, args));
+    uint32_t col0 = half ? K : 0u;
+    std::vector<void*> args = {&K, &seed, &tag, &s->data_len, &s->params_len, &s->params, &cmp, &act, &pitch, &lp,
+                               &s->accept, &s->blk_sums, &cA, &cB, &cC, &step, &accumulate, &kb, &ke};
+    if (m->mirror) { args.push_back(&cmp_a); args.push_back(&act_a); }
+    if (m->peers) { args.push_back(&s->peer_tab); args.push_back(&col0); s->soa_stale = m->mirror; }
+    TRY(launch(m->e, m->f_accu, cdiv(ke - kb, m->e->wgs), m->e->wgs, args.data()));
     return exchange_half(s, half);
 }
 

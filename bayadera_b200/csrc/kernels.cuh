@@ -164,16 +164,23 @@ __global__ void k_minmax_decode(uint32_t dim, const uint32_t* __restrict__ mm, f
 // Fast path: t' = (x-lo) * (BINS/range) differs from the defining expression by a few ulp, so floor(t') is the
 // defining bin unless t' sits within 1e-6 relative of an integer; only then (and for NaN / out-of-range values)
 // is the IEEE division evaluated.  The counts stay bit-exact while the common case costs a multiply.
-__device__ __forceinline__ uint32_t hist_bin(float x, float lo, float range, float fbins, uint32_t bins) {
-    const float d = __fsub_rn(x, lo);
-    const float ta = d * __fdividef(fbins, range);
-    if (ta > 0.5f && ta < fbins - 0.5f && fabsf(ta - rintf(ta)) > 1e-6f * (ta + 1.0f)) return (uint32_t)ta;
+__device__ __noinline__ uint32_t hist_bin_exact(float d, float range, float fbins, uint32_t bins) {
     const float t = __fmul_rn(__fdiv_rn(d, range), fbins);
     uint32_t b;
     if (!(t > 0.0f)) b = 0;
     else if (t >= fbins) b = bins - 1;
     else b = (uint32_t)t;
     return b;
+}
+
+// scale = BINS/range (any rounding), guard = BINS - 0.5
+__device__ __forceinline__ uint32_t hist_bin(float x, float lo, float range, float fbins, uint32_t bins,
+                                             float scale, float guard) {
+    const float d = __fsub_rn(x, lo);
+    const float ta = d * scale;
+    const bool interior = ta > 0.5f && ta < guard && fabsf(ta - rintf(ta)) > fmaf(1e-6f, ta, 1e-6f);
+    if (__builtin_expect(interior, 1)) return (uint32_t)ta;
+    return hist_bin_exact(d, range, fbins, bins);     // kept out of line: rare, and it would be if-converted
 }
 
 // grid = (chunks, dim).  Shared memory: NSUB privatised sub-histograms of `bins`
@@ -189,6 +196,7 @@ __global__ void k_hist_soa(const float* __restrict__ xs, uint64_t pitch, uint64_
     __syncthreads();
     const float lo = limits[2 * d], hi = limits[2 * d + 1];
     const float range = __fsub_rn(hi, lo), fbins = (float)bins;
+    const float scale = __fdividef(fbins, range), guard = fbins - 0.5f;
     uint32_t* mine = sh + ((threadIdx.x >> 5) % nsub) * bins;
     const float* row = xs + (size_t)d * pitch;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -199,16 +207,16 @@ __global__ void k_hist_soa(const float* __restrict__ xs, uint64_t pitch, uint64_
         const float4* row4 = reinterpret_cast<const float4*>(row);
         for (uint64_t q = i; q < n4; q += stride) {
             const float4 v = __ldg(row4 + q);
-            atomicAdd(&mine[hist_bin(v.x, lo, range, fbins, bins)], 1u);
-            atomicAdd(&mine[hist_bin(v.y, lo, range, fbins, bins)], 1u);
-            atomicAdd(&mine[hist_bin(v.z, lo, range, fbins, bins)], 1u);
-            atomicAdd(&mine[hist_bin(v.w, lo, range, fbins, bins)], 1u);
+            atomicAdd(&mine[hist_bin(v.x, lo, range, fbins, bins, scale, guard)], 1u);
+            atomicAdd(&mine[hist_bin(v.y, lo, range, fbins, bins, scale, guard)], 1u);
+            atomicAdd(&mine[hist_bin(v.z, lo, range, fbins, bins, scale, guard)], 1u);
+            atomicAdd(&mine[hist_bin(v.w, lo, range, fbins, bins, scale, guard)], 1u);
         }
         for (uint64_t q = (n4 << 2) + i; q < n; q += stride)
-            atomicAdd(&mine[hist_bin(row[q], lo, range, fbins, bins)], 1u);
+            atomicAdd(&mine[hist_bin(row[q], lo, range, fbins, bins, scale, guard)], 1u);
     } else {
         for (uint64_t q = i; q < n; q += stride)
-            atomicAdd(&mine[hist_bin(row[q], lo, range, fbins, bins)], 1u);
+            atomicAdd(&mine[hist_bin(row[q], lo, range, fbins, bins, scale, guard)], 1u);
     }
     __syncthreads();
     for (uint32_t b = threadIdx.x; b < bins; b += blockDim.x) {
@@ -485,6 +493,30 @@ __global__ void k_glm_finish_ld(uint32_t n, uint32_t chunks, uint32_t ldp, const
     double s = 0.0;
     for (uint32_t c = 0; c < chunks; c++) s += partial[(size_t)c * ldp + k];
     sp[k] = s;
+}
+
+// ---------------------------------------------------------------------------
+// Multi-GPU mode A over peer memory.  PeerTable mirrors bay_peers_t of the NVRTC program (stretch_program.inc).
+// ---------------------------------------------------------------------------
+struct PeerTable {
+    unsigned long long base[8];
+    unsigned long long lp_off, xa_off;
+    uint32_t n, self;
+};
+
+// Barrier between half-steps: lane r publishes `epoch` into slot [rank] of rank r's flags (after a system-scope
+// fence, so the stretch kernel's peer stores are ordered before it) and waits for slot [r] of its own flags.
+__global__ void k_peer_barrier(PeerTable t, uint64_t flags_off, uint32_t rank, uint32_t epoch) {
+    const uint32_t r = threadIdx.x;
+    if (r >= t.n) return;
+    __threadfence_system();
+    uint32_t* remote = reinterpret_cast<uint32_t*>(t.base[r]) + flags_off + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(t.base[rank]) + flags_off + r;
+    uint32_t seen;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+    } while ((int32_t)(seen - epoch) < 0);
 }
 
 }  // namespace bay

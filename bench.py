@@ -403,8 +403,11 @@ def main():
                            "parallelism": "single GPU" if world == 1 else (
                                f"rows sharded over {world} GPUs, walkers replicated, NCCL all-reduce of per-walker sums"
                                if sharded else
-                               f"one ensemble of {W_global} walkers partitioned over {world} GPUs, NCCL all-gather of the "
-                               "updated slice every half-step"),
+                               f"one ensemble of {W_global} walkers partitioned over {world} GPUs, " + (
+                                   "NCCL all-gather of the updated slice every half-step"
+                                   if os.environ.get("BAY_P2P", "1").startswith("0") else
+                                   "accepted walkers stored into every peer's ensemble by the stretch kernel (NVLink "
+                                   "peer memory) + flag barrier every half-step")),
                            "l2": "flushed between timed steps (256 MiB write)",
                            "kernel": {"name": kernel_name, **info}},
                 "e2e": {"value": e2e_value, "unit": UNIT,
