@@ -966,8 +966,11 @@ static int half_accu(bay_sampler* s, int half, uint32_t seed, uint32_t tag, floa
 // co-resident — the launch-latency-bound regime of small ensembles.  BAY_LOOP=0 disables it.
 static bool loop_usable(const bay_sampler* s, int64_t n) {
     const bay_model* m = s->m;
-    if (m->glm || !m->f_loop || n < 2 || partitioned(s)) return false;
-    if ((int64_t)cdiv(s->H, m->loop_block) > m->loop_capacity) return false;
+    if (m->glm || !m->f_loop || n < 2) return false;
+    if (partitioned(s) && !m->peers) return false;   // the NCCL exchange needs a kernel boundary per half-step
+    uint32_t kb, ke;
+    my_slice(s, &kb, &ke);
+    if ((int64_t)cdiv(ke - kb, m->loop_block) > m->loop_capacity) return false;
     static const int off = [] { const char* env = getenv("BAY_LOOP"); return (env && env[0] == '0') ? 1 : 0; }();
     return !off;
 }
@@ -993,10 +996,21 @@ static int move_bare_loop(bay_sampler* s, int64_t n, const float* betas, float c
         uint32_t n_steps = (uint32_t)chunk;
         float beta_const = s->beta;
         const float* bptr = betas_dev ? betas_dev + done : nullptr;
-        void* args[] = {&K, &seed, &s->data_len, &s->params_len, &s->params, &s->xs, &pitch, &s->lp, &cA, &cB, &cC,
-                        &bptr, &beta_const, &step0, &n_steps, &s->loop_bar, &s->xa};   // xa only with BAY_MIRROR
-        CUresult cr = g_cu.LaunchCooperativeKernel(m->f_loop, cdiv(K, m->loop_block), 1, 1, m->loop_block, 1, 1, 0,
-                                                   reinterpret_cast<CUstream>(e->stream), args);
+        uint32_t kb, ke, epoch0 = s->peer_epoch;
+        my_slice(s, &kb, &ke);
+        std::vector<void*> args = {&K, &seed, &s->data_len, &s->params_len, &s->params, &s->xs, &pitch, &s->lp, &cA, &cB,
+                                   &cC, &bptr, &beta_const, &step0, &n_steps, &s->loop_bar, &kb, &ke};
+        if (m->mirror) args.push_back(&s->xa);
+        if (m->peers) {
+            // the loop's grid barrier also spans the GPUs: one flag epoch per half-step
+            args.push_back(&s->peer_tab);
+            args.push_back(&s->peer_flags_off);
+            args.push_back(&epoch0);
+            s->peer_epoch += 2u * n_steps;
+            s->soa_stale = m->mirror;
+        }
+        CUresult cr = g_cu.LaunchCooperativeKernel(m->f_loop, cdiv(ke - kb, m->loop_block), 1, 1, m->loop_block, 1, 1, 0,
+                                                   reinterpret_cast<CUstream>(e->stream), args.data());
         if (cr != CUDA_SUCCESS) return cu_fail(cr, "cuLaunchCooperativeKernel(bay_stretch_loop)");
         g_launches++;
         s->bare_counter += (uint32_t)chunk;
