@@ -302,7 +302,7 @@ struct bay_sampler {
     double* glm_sp = nullptr;                 // W: sum_rows softplus
     double* lp64 = nullptr;                   // W
     uint32_t glm_chunks = 0, glm_rows_per_chunk = 0;
-    // tensor-core variant (DIM == 64): bf16 hi/lo planes of the dataset and of the walker block + TMA maps
+    // tensor-core variant (DIM <= 64): bf16 hi/lo planes of the dataset and of the walker block + TMA maps
     bool glm_tc = false;
     __nv_bfloat16 *glm_xh = nullptr, *glm_xl = nullptr, *glm_ah = nullptr, *glm_al = nullptr;
     CUtensorMap glm_map_xh, glm_map_xl;

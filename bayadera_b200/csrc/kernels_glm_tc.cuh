@@ -284,12 +284,13 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
 constexpr float LOG2E = 1.4426950408889634f;
 
 // points (SoA, dim 64 x n, pitch) -> bf16 hi/lo planes [n][64] (row = walker) of theta * log2(e), the A operand
-__global__ void k_glm_split_points(const float* __restrict__ pts, uint32_t pitch, uint32_t n,
+__global__ void k_glm_split_points(const float* __restrict__ pts, uint32_t pitch, uint32_t n, uint32_t dim,
                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;    // e = k*64 + i, coalesced stores
     if (e >= n * KD) return;
     const uint32_t k = e / KD, i = e % KD;
-    const float x = __fmul_rn(pts[(size_t)i * pitch + k], LOG2E);
+    // dim < 64: the K extent is zero-padded (the MMA cost is hidden under the MUFU-bound epilogue anyway)
+    const float x = i < dim ? __fmul_rn(pts[(size_t)i * pitch + k], LOG2E) : 0.0f;
     const __nv_bfloat16 h = __float2bfloat16_rn(x);
     hi[e] = h;
     lo[e] = __float2bfloat16_rn(x - __bfloat162float(h));
@@ -300,27 +301,27 @@ __global__ void k_glm_split_points(const float* __restrict__ pts, uint32_t pitch
 // stride over the partial rows, then a fixed shuffle tree (deterministic: same order on every run and rank).
 __global__ void k_glm_finish_tc(uint32_t n, uint32_t chunks, uint32_t ldp, const double* __restrict__ partial,
                                 const double* __restrict__ sx, const float* __restrict__ pts, uint32_t pitch,
-                                double* __restrict__ sp) {
+                                uint32_t dim, double* __restrict__ sp) {
     const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (k >= n) return;
     double s = 0.0;
     for (uint32_t c = lane; c < chunks; c += 32) s += partial[(size_t)c * ldp + k];
-    for (uint32_t i = lane; i < KD; i += 32)
+    for (uint32_t i = lane; i < dim; i += 32)
         s += 0.5 * 0.6931471805599453 * sx[i] * (double)__fmul_rn(pts[(size_t)i * pitch + k], LOG2E);
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) sp[k] = s;
 }
 
-// dataset rows [y, x_1..x_64] (stride 65) -> bf16 hi/lo planes [rows][64]
-__global__ void k_glm_split_rows(const float* __restrict__ data, uint64_t rows,
+// dataset rows [y, x_1..x_dim] (stride dim + 1) -> bf16 hi/lo planes [rows][64], zero-padded past dim
+__global__ void k_glm_split_rows(const float* __restrict__ data, uint64_t rows, uint32_t dim,
                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
     const uint64_t total = rows * KD;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
         const uint64_t r = e / KD;
         const uint32_t i = (uint32_t)(e % KD);
-        const float x = data[r * (KD + 1) + 1 + i];
+        const float x = i < dim ? data[r * (dim + 1) + 1 + i] : 0.0f;
         const __nv_bfloat16 h = __float2bfloat16_rn(x);
         hi[e] = h;
         lo[e] = __float2bfloat16_rn(x - __bfloat162float(h));
