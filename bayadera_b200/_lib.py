@@ -95,6 +95,10 @@ SIGNATURES = {
     "bay_model_density": (C.c_int, [_vp, _vp, _i64, _f32, _i64, C.c_int, _f32]),
     "bay_model_evidence": (C.c_int, [_vp, _vp, _i64, _f32, _i64, C.POINTER(C.c_double)]),
     "bay_direct_sample": (C.c_int, [_vp, C.c_int, _i32, _f32, C.c_int, _i64, _vp, C.c_int]),
+    "bay_hdi": (C.c_int, [_vp, C.c_double, _vp, _vp, _vp, C.c_int]),
+    "bay_hdi_histogram": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp, _vp, C.c_int]),
+    "bay_mix": (C.c_int, [_vp, _i64, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                          C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "bay_launch_count": (_i64, []),
 }
 

@@ -496,6 +496,67 @@ __global__ void k_glm_finish_ld(uint32_t n, uint32_t chunks, uint32_t ldp, const
 }
 
 // ---------------------------------------------------------------------------
+// HDI (C/util.clj:52-100): hdi-rank-count + hdi-bins + hdi-regions of every histogram column,
+// one CTA per dimension.  pdf / ranks: bins x dim column-major, limits: 2 x dim.  The mass accumulation is the
+// reference's sequential double loop (one thread; 256 shared-memory reads); asum is an fp32 accumulation like the
+// reference's BLAS call (sequential order here).
+//   counts[d]   = smallest number of ranked bins whose mass reaches mass * sum(pdf)   (or forced[d] if >= 0)
+//   regions     = [lo0 hi0 lo1 hi1 ...] of the maximal runs of selected bins, 2 * max_regions floats per dimension
+// dynamic shared memory: 3 * bins words
+// ---------------------------------------------------------------------------
+__global__ void k_hdi(uint32_t bins, const float* __restrict__ limits, const float* __restrict__ pdf,
+                      const float* __restrict__ ranks, double mass, const int32_t* __restrict__ forced,
+                      int32_t* __restrict__ counts, int32_t* __restrict__ nregions, float* __restrict__ regions,
+                      uint32_t max_regions) {
+    extern __shared__ float hdi_sm[];
+    float* p = hdi_sm;
+    uint32_t* rk = reinterpret_cast<uint32_t*>(hdi_sm + bins);
+    uint32_t* sel = rk + bins;
+    __shared__ uint32_t cnt_s;
+    const uint32_t d = blockIdx.x;
+    for (uint32_t i = threadIdx.x; i < bins; i += blockDim.x) {
+        p[i] = pdf[(size_t)d * bins + i];
+        const uint32_t r = (uint32_t)ranks[(size_t)d * bins + i];
+        rk[i] = r < bins ? r : bins - 1;
+        sel[i] = 0u;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t cnt = 0;
+        if (forced && forced[d] >= 0) {
+            cnt = (uint32_t)forced[d] < bins ? (uint32_t)forced[d] : bins;
+        } else {
+            float total = 0.0f;   // Neanderthal asum of a float vector: fp32 accumulation (sequential here)
+            for (uint32_t i = 0; i < bins; i++) total = __fadd_rn(total, fabsf(p[i]));
+            const double density = mass * (double)total;
+            double acc = 0.0;
+            while (cnt < bins && acc < density) acc += (double)p[rk[cnt++]];
+        }
+        cnt_s = cnt;
+        counts[d] = (int32_t)cnt;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < cnt_s; i += blockDim.x) sel[rk[i]] = 1u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double lower = (double)limits[2 * d], upper = (double)limits[2 * d + 1];
+        const double bw = (upper - lower) / (double)bins;
+        uint32_t n = 0;
+        for (uint32_t b = 0; b < bins; b++) {
+            if (!sel[b]) continue;
+            const uint32_t start = b;
+            while (b + 1 < bins && sel[b + 1]) b++;
+            if (n < max_regions) {
+                regions[((size_t)d * max_regions + n) * 2] = (float)(lower + bw * (double)start);
+                regions[((size_t)d * max_regions + n) * 2 + 1] = (float)(lower + bw * ((double)b + 1.0));
+            }
+            n++;
+        }
+        nregions[d] = (int32_t)n;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Multi-GPU mode A over peer memory.  PeerTable mirrors bay_peers_t of the NVRTC program (stretch_program.inc).
 // ---------------------------------------------------------------------------
 struct PeerTable {

@@ -279,6 +279,37 @@ class B200Stretch:
         check(self._L.bay_histogram_counts(self._h, out))
         return out.reshape(self.DIM, self.WGS)
 
+    def hdi(self, mass: float = 0.95, max_regions: Optional[int] = None) -> list:
+        """``hdi`` (util.clj:102-110) of every dimension of the LATEST ``histogram()``, computed on the device
+        (SURVEY §8f row 4).  Returns one ``(count, regions)`` per dimension, regions a (k, 2) array of [lo, hi]."""
+        max_regions = (self.WGS + 1) // 2 if max_regions is None else max_regions   # runs of bins: at most half
+        counts = np.zeros(self.DIM, dtype=np.int32)
+        nreg = np.zeros(self.DIM, dtype=np.int32)
+        regions = np.zeros((self.DIM, max_regions, 2), dtype=np.float32)
+        check(self._L.bay_hdi(self._h, float(mass), ptr(counts), ptr(nreg), ptr(regions), max_regions))
+        return [(int(counts[d]), regions[d, :min(int(nreg[d]), max_regions)].copy()) for d in range(self.DIM)]
+
+    def mix(self, options: Optional[dict] = None) -> dict:
+        """``mix!`` (mcmc.clj:66-101) in one boundary crossing (``bay_mix``); same options and result map as
+        ``bayadera_b200.mcmc.mix``, for the three built-in cooling schedules."""
+        from . import mcmc
+        o = dict(options or {})
+        sched = o.get("cooling-schedule", mcmc.minus_n)
+        power = 1.0
+        if sched is mcmc.minus_n:
+            kind = 0
+        elif sched is mcmc.sqrt_n:
+            kind = 1
+        elif getattr(sched, "pow_n_power", None) is not None:
+            kind, power = 2, float(sched.pow_n_power)
+        else:
+            return mcmc.mix(self, o)          # arbitrary host schedule: the protocol-call loop
+        a, r1, r2 = C.c_double(), C.c_double(), C.c_double()
+        check(self._L.bay_mix(self._h, int(o.get("step", 64)), float(o.get("dimension-power", 0.8)), kind, power,
+                              float(o.get("a", 2.0)), float(o.get("min-acc-rate", 0.2)),
+                              float(o.get("max-acc-rate", 0.5)), C.byref(a), C.byref(r1), C.byref(r2)))
+        return {"a": a.value, "acc-rate": r1.value, "acc-rate-2.0": r2.value}
+
     def mean(self) -> np.ndarray:
         out = np.zeros(self.DIM, dtype=np.float32)
         check(self._L.bay_mean(self._h, out))
@@ -388,6 +419,21 @@ class B200AcorEngine:
         lag = C.c_int64()
         check(self._L.bay_acor(self.factory._h, s.reshape(-1), dim, n, ptr(tau), ptr(mean), ptr(sigma), C.byref(lag)))
         return Autocorrelation(tau, mean, sigma, n, lag.value)
+
+
+def hdi_histogram(factory: B200BayaderaFactory, histogram: "Histogram", mass: float = 0.95,
+                  forced_counts=None, max_regions: Optional[int] = None) -> list:
+    """hdi-rank-count + hdi-regions (util.clj:52-100) of every column of a caller-held ``Histogram`` on the device."""
+    lim, pdf, ranks = _f32(histogram.limits), _f32(histogram.pdf), _f32(histogram.bin_ranks)
+    dim, bins = pdf.shape
+    max_regions = (bins + 1) // 2 if max_regions is None else max_regions
+    counts = np.zeros(dim, dtype=np.int32)
+    nreg = np.zeros(dim, dtype=np.int32)
+    regions = np.zeros((dim, max_regions, 2), dtype=np.float32)
+    forced = None if forced_counts is None else np.ascontiguousarray(forced_counts, dtype=np.int32)
+    check(factory._L.bay_hdi_histogram(factory._h, bins, dim, ptr(lim), ptr(pdf), ptr(ranks), float(mass), ptr(forced),
+                                       ptr(counts), ptr(nreg), ptr(regions), max_regions))
+    return [(int(counts[d]), regions[d, :min(int(nreg[d]), max_regions)].copy()) for d in range(dim)]
 
 
 def launch_count() -> int:

@@ -45,7 +45,10 @@ def sqrt_n(temp: float) -> Callable[[int], float]:
 
 
 def pow_n(power: float) -> Callable[[float], Callable[[int], float]]:
-    return lambda temp: (lambda i: math.pow(temp - i, power))
+    def schedule(temp: float) -> Callable[[int], float]:
+        return lambda i: math.pow(temp - i, power)
+    schedule.pow_n_power = power          # lets the engine run this schedule inside bay_mix
+    return schedule
 
 
 def minus_n(temp: float) -> Callable[[int], float]:

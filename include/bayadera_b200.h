@@ -189,6 +189,25 @@ int bay_model_evidence(bay_model *m, const float *params_host, int64_t params_co
 int bay_direct_sample(bay_engine *e, int family, int32_t seed, const float *params_host, int nparams, int64_t n,
                       void *out, int out_is_device);
 
+/* ---- next row f-4: HDI on the device, mix! in one call ------------------------------------------------------
+ * hdi (C/util.clj:102-110 = hdi-rank-count :52-65 + hdi-bins :67-83 + hdi-regions :85-100; C = the reference's
+ * src/clojure/uncomplicate/bayadera/) for EVERY dimension of the sampler's latest histogram!, which is still on the
+ * device.  counts[D]: number of ranked bins holding `mass`; nregions[D]; regions: D x (2 * max_regions) floats,
+ * [lo0 hi0 lo1 hi1 ...] per dimension (regions beyond max_regions are counted, not stored). */
+int bay_hdi(bay_sampler *s, double mass, int32_t *counts, int32_t *nregions, float *regions, int max_regions);
+/* The same for caller-held Histogram columns (host arrays, column = dimension: limits 2 x dim, pdf and bin-ranks
+ * bins x dim).  forced_counts != NULL with an entry >= 0 skips hdi-rank-count for that dimension (the
+ * (hdi-regions limits bin-rank hdi-cnt) arity). */
+int bay_hdi_histogram(bay_engine *e, int bins, int dim, const float *limits_host, const float *pdf_host,
+                      const float *ranks_host, double mass, const int32_t *forced_counts, int32_t *counts,
+                      int32_t *nregions, float *regions, int max_regions);
+/* mix! (C/mcmc.clj:66-101): anneal step*D^dimension_power steps on `schedule` (0 minus-n, 1 sqrt-n, 2 pow-n with
+ * schedule_power), tune a towards an acceptance rate in [min_acc, max_acc] with up to step+1 acc-rate! probes,
+ * burn in.  One boundary crossing instead of the reference's ~70 protocol calls.  Outputs = the reference's map
+ * {:a :acc-rate :acc-rate-2.0}. */
+int bay_mix(bay_sampler *s, int64_t step, double dimension_power, int schedule, double schedule_power, double a,
+            double min_acc, double max_acc, double *out_a, double *out_acc_rate, double *out_acc_rate_2);
+
 /* profiling counters: kernels launched by this library on the calling process */
 int64_t bay_launch_count(void);
 

@@ -97,3 +97,18 @@ def acor_fixture(n: int) -> np.ndarray:
     data = np.load(GOLDEN_DIR / "acor_fixtures.npz")[f"acor_{n}"].astype(np.float32)
     m = np.stack([data, ACOR[n]["row1"](data).astype(np.float32)], axis=1)  # n x 2
     return np.ascontiguousarray(m, dtype=np.float32)
+
+
+# HDI helpers: T/util_test.clj:21-57 — 79 bins on [1, 7]
+HDI_LIMITS = (1.0, 7.0)
+HDI_PDF = (0.02, 0.01, 0.04, 0.05, 0.07, 0.01, 0.2, 0.1, 0.3, 0.1, 0.02) + (0.01,) * 68
+HDI_BIN_RANK = (8, 6, 7, 9, 4, 3, 2, 0, 10, 1, 5) + tuple(range(11, 79))
+# (mass, divide-by-asum?) -> hdi-rank-count   (util_test.clj:35-41)
+HDI_RANK_COUNTS = [(0.1, False, 1), (0.3, True, 1), (0.3, False, 2), (0.7, True, 4), (0.86, True, 7), (0.9, True, 9),
+                   (0.95, True, 14)]
+# hdi-cnt -> hdi-bins   (util_test.clj:45-50)
+HDI_BINS = {1: [8.0, 8.0], 2: [6.0, 6.0, 8.0, 8.0], 5: [4.0, 4.0, 6.0, 9.0], 6: [3.0, 4.0, 6.0, 9.0], 12: [0.0, 11.0],
+            15: [0.0, 14.0]}
+# hdi-cnt -> (regions column-major [lo0 hi0 lo1 hi1], nrm2 tolerance)   (util_test.clj:54-58)
+HDI_REGIONS = {1: ([1.61, 1.68], 0.005), 2: ([1.46, 1.53, 1.61, 1.68], 0.007), 5: ([1.30, 1.38, 1.46, 1.76], 0.006),
+               6: ([1.23, 1.38, 1.46, 1.76], 0.006), 12: ([1.00, 1.91], 0.002)}

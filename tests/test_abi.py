@@ -91,3 +91,27 @@ def test_parameter_vectors():
     u = v[8:].reshape(8, 8).astype(np.float64)
     assert np.allclose(u, np.triu(u))
     assert np.allclose(np.linalg.inv(u.T @ u), sigma, rtol=2e-3, atol=1e-3)
+
+
+# ---- util.clj host helpers (T/util_test.clj goldens) ----------------------------------------------------------
+def test_hdi_host_helpers_match_reference_goldens():
+    import goldens as G
+    from bayadera_b200 import util
+    pdf = np.asarray(G.HDI_PDF, dtype=np.float32)
+    rank = np.asarray(G.HDI_BIN_RANK, dtype=np.float32)
+    asum = util.asum(pdf)
+    for mass, scaled, want in G.HDI_RANK_COUNTS:
+        assert util.hdi_rank_count(rank, pdf, mass / asum if scaled else mass) == want
+    for cnt, want in G.HDI_BINS.items():
+        assert util.hdi_bins(rank, cnt) == want
+    for cnt, (want, tol) in G.HDI_REGIONS.items():
+        got = util.hdi_regions(G.HDI_LIMITS, rank, cnt).reshape(-1)
+        assert np.linalg.norm(got - np.asarray(want)) < tol
+    assert util.bin_mapper(79, 1.0, 7.0)(0) == pytest.approx(1.0 + 0.5 * 6.0 / 79)
+    assert util.range_mapper(0.0, 1.0, 10.0, 20.0)(0.25) == 12.5
+
+
+def test_mix_schedules_expose_their_kind():
+    from bayadera_b200 import mcmc
+    assert mcmc.pow_n(0.5).pow_n_power == 0.5
+    assert mcmc.pow_n(0.5)(9.0)(5) == 2.0 and mcmc.sqrt_n(9.0)(5) == 2.0 and mcmc.minus_n(9.0)(5) == 4.0

@@ -78,3 +78,69 @@ def test_beta_binomial_posterior_density_and_evidence(factory):
     assert abs(ev / 1.6357453252754427e-15 - 1) < 1e-4
     lik_vals = lik.density(models.binomial_lik_params(n, z), x)
     assert abs(float(lik_vals.astype(np.float64).mean()) / ev - 1) < 1e-5
+
+
+# ---- row f-4: HDI on the device, mix! in one call ---------------------------------------------------------------
+def test_hdi_device_reference_goldens(factory):
+    """T/util_test.clj:21-58 through bay_hdi_histogram (79 bins on [1, 7])."""
+    from bayadera_b200 import util
+    from bayadera_b200.engine import Histogram, hdi_histogram
+    pdf, rank = f32(G.HDI_PDF), f32(G.HDI_BIN_RANK)
+    h = Histogram(f32([G.HDI_LIMITS]), pdf[None, :], rank[None, :])
+    asum = util.asum(pdf)
+    for mass, scaled, want in G.HDI_RANK_COUNTS:
+        (cnt, _), = hdi_histogram(factory, h, mass / asum if scaled else mass)
+        assert cnt == want, (mass, scaled, cnt)
+    for cnt, want in G.HDI_BINS.items():
+        (got_cnt, regions), = hdi_histogram(factory, h, forced_counts=[cnt])
+        assert got_cnt == cnt
+        bw = (G.HDI_LIMITS[1] - G.HDI_LIMITS[0]) / 79
+        bins = np.stack([(regions[:, 0] - 1.0) / bw, (regions[:, 1] - 1.0) / bw - 1.0], axis=1).reshape(-1)
+        assert np.allclose(bins, want, atol=1e-4), (cnt, bins)
+    for cnt, (want, tol) in G.HDI_REGIONS.items():
+        (_, regions), = hdi_histogram(factory, h, forced_counts=[cnt])
+        assert np.linalg.norm(regions.reshape(-1) - np.asarray(want)) < tol
+        assert np.allclose(regions, util.hdi_regions(G.HDI_LIMITS, rank, cnt), atol=1e-6)
+
+
+def test_hdi_of_sampler_histogram_matches_host_definition(factory):
+    """B200Stretch.hdi (device, all dimensions at once) == util.clj's host definition applied to the same histogram."""
+    from bayadera_b200 import util
+    # the built-in Gaussian in 1-D plus the 30-D hierarchical model cover single- and many-dimension histograms
+    for model, params, limits, walkers in [
+            (models.GAUSSIAN, f32([3, 1]), f32([-7, 7]), 4096),
+            (models.therapeutic_touch_model(), models.therapeutic_touch_data(),
+             models.therapeutic_touch_model().limits_array(), 2048)]:
+        s = factory.mcmc_factory(model).create_sampler(7, walkers, params).init_position(8, limits)
+        s.burn_in(200, 2.0)
+        h = s.histogram(4)
+        got = s.hdi(0.95)
+        assert len(got) == model.dimension
+        for d, (cnt, regions) in enumerate(got):
+            assert cnt == util.hdi_rank_count(h.bin_ranks[d], h.pdf[d], 0.95)
+            assert np.allclose(regions, util.hdi(h, d, 0.95), rtol=1e-6, atol=1e-6)
+            assert 1 <= cnt <= G.WGS and (regions[:, 0] < regions[:, 1]).all()
+    # Gaussian(3,1): the 95 % HDI is about [3 - 1.96, 3 + 1.96]
+    s = factory.mcmc_factory(models.GAUSSIAN).create_sampler(7, 8192, f32([3, 1])).init_position(8, f32([-7, 7]))
+    s.burn_in(300, 2.0)
+    s.histogram(16)
+    (_, regions), = s.hdi(0.95)
+    assert abs(regions[0, 0] - (3 - 1.96)) < 0.25 and abs(regions[-1, 1] - (3 + 1.96)) < 0.25
+
+
+@pytest.mark.parametrize("schedule", ["minus_n", "sqrt_n", "pow_n"])
+def test_mix_in_one_call_equals_protocol_loop(factory, schedule):
+    """bay_mix == mcmc.mix (C/mcmc.clj:66-101 as ~70 protocol calls): same chain, same tuned a, same rates."""
+    from bayadera_b200 import mcmc
+    sched = {"minus_n": mcmc.minus_n, "sqrt_n": mcmc.sqrt_n, "pow_n": mcmc.pow_n(0.7)}[schedule]
+    model, params = models.GAUSSIAN, f32([200, 1])
+    out = []
+    for one_call in (True, False):
+        s = factory.mcmc_factory(model).create_sampler(3, 2 * G.W, params).init_position(4, f32([180, 220]))
+        opts = {"step": 32, "a": 2.0, "cooling-schedule": sched}   # a = 2 accepts too often in 1-D: the tuner must move it
+        res = s.mix(opts) if one_call else mcmc.mix(s, opts)
+        out.append((res, s.get_state()))
+    (ra, sa), (rb, sb) = out
+    assert ra == rb, (ra, rb)
+    assert ra["a"] > 2.0 and 0.2 <= ra["acc-rate"] < ra["acc-rate-2.0"], ra
+    assert np.array_equal(sa["xs"], sb["xs"]) and np.array_equal(sa["logfn"], sb["logfn"])
