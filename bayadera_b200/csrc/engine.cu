@@ -971,8 +971,8 @@ static bool loop_usable(const bay_sampler* s, int64_t n) {
     uint32_t kb, ke;
     my_slice(s, &kb, &ke);
     if ((int64_t)cdiv(ke - kb, m->loop_block) > m->loop_capacity) return false;
-    static const int off = [] { const char* env = getenv("BAY_LOOP"); return (env && env[0] == '0') ? 1 : 0; }();
-    return !off;
+    const char* env = getenv("BAY_LOOP");
+    return !(env && env[0] == '0');
 }
 
 static int move_bare_loop(bay_sampler* s, int64_t n, const float* betas, float cA, float cB, float cC) {

@@ -385,3 +385,37 @@ def test_sample_small_n_and_processing_elements(factory):
     assert np.array_equal(gpu.sample(10), cpu.sample(10))
     assert factory.processing_elements() % G.WGS == 0 and factory.processing_elements() >= 100 * G.WGS
     assert bb.launch_count() > 0
+
+
+# ---- implementation variants must not change the chain ----------------------------------------------------------
+def _chain_state(factory, model, params, limits, walkers):
+    s = factory.mcmc_factory(model).create_sampler(21, walkers, params).init_position(22, limits)
+    s.burn_in(19, 1.8)
+    s.anneal(mcmc.minus_n(7.0), 7, 2.2)
+    s.sample(walkers)                      # one more bare move
+    st = s.get_state()
+    r = s.run_sampler(64, 2.0)
+    return st, r["acceptance-rate"], s.accu_blocks()
+
+
+VARIANT_CASES = [("gaussian-d1", lambda: (models.GAUSSIAN, f32([3, 1]), f32([-7, 7]), 4096)),
+                 ("touch-d30", lambda: (models.therapeutic_touch_model(), models.therapeutic_touch_data(),
+                                        models.therapeutic_touch_model().limits_array(), 2048)),
+                 ("mvn-d100", lambda: (models.mvn_model(100), models.mvn_params(100)[0],
+                                       models.mvn_model(100).limits_array(), 1024))]
+
+
+@pytest.mark.parametrize("name,case", VARIANT_CASES, ids=[c[0] for c in VARIANT_CASES])
+def test_persistent_loop_and_mirror_do_not_change_the_chain(factory, name, case, monkeypatch):
+    """The persistent step loop (one cooperative launch for n steps) and the AoS mirror of the ensemble are pure
+    implementation choices: chains must be bit-identical with either switched off (BAY_LOOP=0, BAY_MIRROR=0)."""
+    model, params, limits, walkers = case()
+    base = _chain_state(factory, model, params, limits, walkers)
+    for var in ("BAY_LOOP", "BAY_MIRROR"):
+        monkeypatch.setenv(var, "0")
+        other = _chain_state(factory, model, params, limits, walkers)     # the model is recompiled per sampler factory
+        monkeypatch.delenv(var)
+        assert np.array_equal(base[0]["xs"], other[0]["xs"]), (name, var)
+        assert np.array_equal(base[0]["logfn"], other[0]["logfn"], equal_nan=True), (name, var)
+        assert base[1] == other[1], (name, var)
+        assert np.array_equal(base[2][0], other[2][0]) and np.array_equal(base[2][1], other[2][1]), (name, var)
