@@ -91,6 +91,7 @@ struct DriverApi {
     CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
     CUresult (*ModuleUnload)(CUmodule) = nullptr;
     CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*ModuleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*) = nullptr;
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                              unsigned, CUstream, void**, void**) = nullptr;
     CUresult (*LaunchCooperativeKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned,
@@ -155,7 +156,8 @@ int load_driver() {
     std::lock_guard<std::mutex> lk(g_api_mutex);
     if (g_cu.ok) return BAY_OK;
     bool ok = drv("cuModuleLoadData", &g_cu.ModuleLoadData) && drv("cuModuleUnload", &g_cu.ModuleUnload) &&
-              drv("cuModuleGetFunction", &g_cu.ModuleGetFunction) && drv("cuLaunchKernel", &g_cu.LaunchKernel) &&
+              drv("cuModuleGetFunction", &g_cu.ModuleGetFunction) &&
+              drv("cuModuleGetGlobal", &g_cu.ModuleGetGlobal) && drv("cuLaunchKernel", &g_cu.LaunchKernel) &&
               drv("cuLaunchCooperativeKernel", &g_cu.LaunchCooperativeKernel) &&
               drv("cuFuncGetAttribute", &g_cu.FuncGetAttribute) &&
               drv("cuFuncSetAttribute", &g_cu.FuncSetAttribute) &&
@@ -238,6 +240,8 @@ struct bay_engine {
     int nranks = 1, rank = 0;
 };
 
+struct bay_sampler;
+
 struct bay_model {
     bay_engine* e = nullptr;
     CUmodule mod = nullptr;
@@ -249,6 +253,16 @@ struct bay_model {
     bool glm = false;
     bool mirror = false;   // AoS mirror of the ensemble for the partner gather (DIM >= 4, non-GLM)
     bool peers = false;    // kernels store accepted walkers into every rank's ensemble block (multi-GPU mode A)
+    // Constant-parameter variant (stretch_program.inc, BAY_CPARAMS): the same program compiled with the parameter
+    // vector in __constant__ memory; built on demand for samplers whose parameters fit (cparams_try)
+    CUmodule cmod = nullptr;
+    CUfunction c_bare = nullptr, c_accu = nullptr, c_logfn = nullptr, c_loop = nullptr;
+    int c_loop_capacity = 0;
+    int cvar_state = 0;                       // 0 not tried, 1 built, -1 unavailable
+    CUdeviceptr cparams = 0;
+    const bay_sampler* cparams_owner = nullptr;   // whose parameters the constant block holds right now
+    std::vector<std::string> srcs;            // what bay_model_compile was given (to build the variant later)
+    std::string logfn_name;
     int dima = 1;          // mirror row length: DIM rounded up to a multiple of 4
     int dim = 1, params_size = 0;
     uint32_t flags = 0;
@@ -272,6 +286,7 @@ struct bay_sampler {
     bay::PeerTable peer_tab;            // block base on every rank + offsets; passed by value to the kernels
     uint64_t peer_flags_off = 0;        // offset (in 4-byte words) of the barrier flags inside the block
     uint32_t peer_epoch = 0;
+    bool cp = false;                    // runs the constant-parameter kernel variant
     bool soa_stale = false;             // peers forwarded mirror rows only: rebuild xs from xa before a read-out
     void* peer_mapped[8] = {nullptr};   // what cudaIpcOpenMemHandle returned (to close on release)
     float* loop_betas = nullptr;        // per-step inverse temperatures (anneal!)
@@ -428,7 +443,8 @@ static int loop_block_for(int dim, int block) { return dim <= 2 ? 1024 : (dim <=
 // gtx-stretch-factory (G/:747-757): model sources first, engine kernels after;
 // stretch-options (G/:630-633) retargeted to sm_100a.
 static int nvrtc_build(const char* const* srcs, int nsrc, const char* logfn_name, int dim, int wgs, int block,
-                       uint32_t flags, bool peers, bool verbose, std::vector<char>* cubin, std::string* log_out) {
+                       uint32_t flags, bool peers, bool verbose, std::vector<char>* cubin, std::string* log_out,
+                       int cparams = 0) {
     if (!srcs || !logfn_name) return fail(BAY_EINVAL, "NULL argument");
     if (dim < 1 || dim > 4096) return fail(BAY_EINVAL, "dimension %d out of range", dim);
     if (wgs < 32 || wgs > 1024 || (wgs & (wgs - 1))) return fail(BAY_EINVAL, "wgs must be a power of two in [32, 1024], got %d", wgs);
@@ -451,11 +467,22 @@ static int nvrtc_build(const char* const* srcs, int nsrc, const char* logfn_name
         opts.push_back("-DBAY_DIMA=" + std::to_string((dim + 3) / 4 * 4));
     }
     if (peers) opts.push_back("-DBAY_PEERS=1");
+    if (cparams > 0) opts.push_back("-DBAY_CPARAMS=" + std::to_string(cparams));
+    // ensemble traffic policy (stretch_program.inc, BAY_STREAM): large-DIM models keep a per-thread local array and
+    // their parameter block in L1, which the once-touched ensemble data would otherwise evict
+    {
+        int stream = dim >= 16 ? 1 : 0;
+        if (const char* env = getenv("BAY_STREAM")) stream = atoi(env);
+        if (stream) opts.push_back("-DBAY_STREAM=" + std::to_string(stream));
+    }
     // Occupancy floor: a thread holds the whole proposal (DIM floats), so for large DIM ptxas takes 255 registers
     // and only 8 warps fit an SM — the kernel then stalls on load latency (ncu: long_scoreboard).  Asking for more
     // resident CTAs caps the registers and trades L1-resident spills for more warps.  BAY_MINB overrides.
     {
         int minb = 1;   // measured on DIM = 100: 1 and 8 tie (0.86 ms), 4 is worse (L1 thrash by local arrays)
+        // with the parameters out of the LSU's way (BAY_CPARAMS) 3 CTAs = 12 warps at 168 registers is the optimum for
+        // DIM = 100: 1.24 G walker-steps/s against 0.85 G at 8 warps and 0.38 G at 16 (128 registers: spills)
+        if (cparams > 0 && dim >= 64) minb = 3;
         if (const char* env = getenv("BAY_MINB")) minb = atoi(env);
         if (minb > 1) opts.push_back("-DBAY_MINB=" + std::to_string(minb));
     }
@@ -522,6 +549,8 @@ extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsr
     m->mirror = model_wants_mirror(dim, flags);
     m->peers = peers;
     m->dima = (dim + 3) / 4 * 4;
+    for (int i = 0; i < nsrc; i++) m->srcs.emplace_back(srcs[i]);
+    m->logfn_name = logfn_name;
 
     CUresult cr = g_cu.ModuleLoadData(&m->mod, cubin.data());
     if (cr != CUDA_SUCCESS) {
@@ -567,6 +596,7 @@ extern "C" int bay_model_release(bay_model* m) {
     if (!m) return BAY_OK;
     cudaSetDevice(m->e->device);
     if (m->mod && g_cu.ok) g_cu.ModuleUnload(m->mod);
+    if (m->cmod && g_cu.ok) g_cu.ModuleUnload(m->cmod);
     delete m;
     return BAY_OK;
 }
@@ -574,11 +604,65 @@ extern "C" int bay_model_release(bay_model* m) {
 extern "C" int bay_model_kernel_info(bay_model* m, const char* kernel, int* regs, int* local_bytes, int* smem_bytes) {
     if (!m || !kernel) return fail(BAY_EINVAL, "NULL argument");
     CUfunction f = nullptr;
-    CUresult cr = g_cu.ModuleGetFunction(&f, m->mod, kernel);
+    CUresult cr = g_cu.ModuleGetFunction(&f, m->cvar_state == 1 ? m->cmod : m->mod, kernel);   // the variant samplers run
     if (cr != CUDA_SUCCESS) return cu_fail(cr, kernel);
     if (regs) g_cu.FuncGetAttribute(regs, CU_FUNC_ATTRIBUTE_NUM_REGS, f);
     if (local_bytes) g_cu.FuncGetAttribute(local_bytes, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, f);
     if (smem_bytes) g_cu.FuncGetAttribute(smem_bytes, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, f);
+    return BAY_OK;
+}
+
+// ---- constant-parameter kernel variant ------------------------------------------------------------------------
+// A warp evaluates LOGFN for 32 walkers against ONE parameter vector: every lane reads the same address.  Through
+// the LSU such loads cost a wavefront per 4 bytes (ncu on the 100-D Gaussian: 93 wavefronts per 64 FFMAs, L1 data
+// pipe 59 % busy, 0.75 G walker-steps/s); from __constant__ memory they become uniform-datapath loads / FFMA
+// operands (LDCU + FFMA R, R, UR, R) and the same model runs at 1.24 G.  The variant is compiled on first use for
+// samplers that OWN a host-supplied parameter vector of 64..16128 floats (a borrowed device vector may be rewritten
+// by its owner between calls, which a constant copy would not see).  BAY_CPARAMS=0 disables it.
+static const int kCparamsCap = 16128;   // floats; the 64 KB constant bank minus what the program itself needs
+
+static void cparams_try(bay_sampler* s, int64_t params_count) {
+    bay_model* m = s->m;
+    if (m->glm || params_count < 64 || params_count > kCparamsCap) return;
+    if (const char* env = getenv("BAY_CPARAMS")) if (env[0] == '0') return;
+    if (m->cvar_state == 0) {
+        m->cvar_state = -1;
+        std::vector<const char*> srcs;
+        for (auto& t : m->srcs) srcs.push_back(t.c_str());
+        std::vector<char> cubin;
+        if (nvrtc_build(srcs.data(), (int)srcs.size(), m->logfn_name.c_str(), m->dim, m->e->wgs, m->block, m->flags, m->peers,
+                        false, &cubin, nullptr, kCparamsCap) != BAY_OK) return;
+        if (g_cu.ModuleLoadData(&m->cmod, cubin.data()) != CUDA_SUCCESS) { m->cmod = nullptr; return; }
+        size_t bytes = 0;
+        bool ok = g_cu.ModuleGetFunction(&m->c_bare, m->cmod, "bay_stretch_bare") == CUDA_SUCCESS &&
+                  g_cu.ModuleGetFunction(&m->c_accu, m->cmod, "bay_stretch_accu") == CUDA_SUCCESS &&
+                  g_cu.ModuleGetFunction(&m->c_logfn, m->cmod, "bay_logfn") == CUDA_SUCCESS &&
+                  g_cu.ModuleGetFunction(&m->c_loop, m->cmod, "bay_stretch_loop") == CUDA_SUCCESS &&
+                  g_cu.ModuleGetGlobal(&m->cparams, &bytes, m->cmod, "bay_cparams") == CUDA_SUCCESS &&
+                  bytes >= sizeof(float) * kCparamsCap;
+        if (!ok) { g_cu.ModuleUnload(m->cmod); m->cmod = nullptr; return; }
+        int per_sm = 0;
+        if (g_cu.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, m->c_loop, m->loop_block, 0) == CUDA_SUCCESS)
+            m->c_loop_capacity = per_sm * m->e->sm_count;
+        m->cvar_state = 1;
+    }
+    s->cp = m->cvar_state == 1;
+}
+
+static CUfunction fn_bare(const bay_sampler* s) { return s->cp ? s->m->c_bare : s->m->f_bare; }
+static CUfunction fn_accu(const bay_sampler* s) { return s->cp ? s->m->c_accu : s->m->f_accu; }
+static CUfunction fn_logfn(const bay_sampler* s) { return s->cp ? s->m->c_logfn : s->m->f_logfn; }
+static CUfunction fn_loop(const bay_sampler* s) { return s->cp ? s->m->c_loop : s->m->f_loop; }
+static int loop_capacity(const bay_sampler* s) { return s->cp ? s->m->c_loop_capacity : s->m->loop_capacity; }
+
+// The constant block belongs to the module, i.e. to all samplers of the model: (re)load it when another sampler's
+// parameters are in it.  Stream-ordered, so kernels already queued keep the values they were launched with.
+static int bind_params(bay_sampler* s) {
+    bay_model* m = s->m;
+    if (!s->cp || m->cparams_owner == s) return BAY_OK;
+    CK(cudaMemcpyAsync(reinterpret_cast<void*>(m->cparams), s->params, sizeof(float) * ((size_t)s->data_len + s->params_len),
+                       cudaMemcpyDeviceToDevice, m->e->stream));
+    m->cparams_owner = s;
     return BAY_OK;
 }
 
@@ -753,6 +837,7 @@ extern "C" int bay_sampler_create(bay_model* m, int32_t seed, int64_t walkers, c
         return fail(BAY_ECUDA, "params upload failed: %s", cudaGetErrorString(ce));
     }
     s->own_params = true;
+    cparams_try(s, params_count);
     if (m->glm) {
         int r = glm_setup(s);
         if (r != BAY_OK) { bay_sampler_release(s); return r; }
@@ -780,6 +865,7 @@ extern "C" int bay_sampler_release(bay_sampler* s) {
     cudaSetDevice(s->m->e->device);
     cudaStreamSynchronize(s->m->e->stream);
     if (s->own_params) cudaFree(s->params);
+    if (s->m->cparams_owner == s) s->m->cparams_owner = nullptr;
     glm_release(s);
     peer_block_release(s);   // clears xs / lp / xa when they live in the shared block
     void* bufs[] = {s->xs, s->lp, s->accept, s->blk_sums, s->accept_total, s->means, s->hist_counts, s->mm,
@@ -821,7 +907,8 @@ static int launch_logfn_all(bay_sampler* s) {
     if (m->glm) return glm_logfn_all(s);
     uint32_t n = (uint32_t)s->W, pitch = (uint32_t)s->W;
     void* args[] = {&n, &s->data_len, &s->params_len, &s->params, &s->xs, &pitch, &s->lp};
-    return launch(m->e, m->f_logfn, cdiv(n, m->block), m->block, args);
+    TRY(bind_params(s));
+    return launch(m->e, fn_logfn(s), cdiv(n, m->block), m->block, args);
 }
 
 // init-position! [seed limits] G/:409-418
@@ -937,7 +1024,8 @@ static int half_bare(bay_sampler* s, int half, uint32_t seed, uint32_t tag, floa
                                &cA, &cB, &cC, &beta, &step, &kb, &ke};
     if (m->mirror) { args.push_back(&cmp_a); args.push_back(&act_a); }
     if (m->peers) { args.push_back(&s->peer_tab); args.push_back(&col0); s->soa_stale = m->mirror; }
-    TRY(launch(m->e, m->f_bare, cdiv(ke - kb, m->block), m->block, args.data()));
+    TRY(bind_params(s));
+    TRY(launch(m->e, fn_bare(s), cdiv(ke - kb, m->block), m->block, args.data()));
     return exchange_half(s, half);
 }
 
@@ -958,7 +1046,8 @@ static int half_accu(bay_sampler* s, int half, uint32_t seed, uint32_t tag, floa
                                &s->accept, &s->blk_sums, &cA, &cB, &cC, &step, &accumulate, &kb, &ke};
     if (m->mirror) { args.push_back(&cmp_a); args.push_back(&act_a); }
     if (m->peers) { args.push_back(&s->peer_tab); args.push_back(&col0); s->soa_stale = m->mirror; }
-    TRY(launch(m->e, m->f_accu, cdiv(ke - kb, m->e->wgs), m->e->wgs, args.data()));
+    TRY(bind_params(s));
+    TRY(launch(m->e, fn_accu(s), cdiv(ke - kb, m->e->wgs), m->e->wgs, args.data()));
     return exchange_half(s, half);
 }
 
@@ -970,7 +1059,7 @@ static bool loop_usable(const bay_sampler* s, int64_t n) {
     if (partitioned(s) && !m->peers) return false;   // the NCCL exchange needs a kernel boundary per half-step
     uint32_t kb, ke;
     my_slice(s, &kb, &ke);
-    if ((int64_t)cdiv(ke - kb, m->loop_block) > m->loop_capacity) return false;
+    if ((int64_t)cdiv(ke - kb, m->loop_block) > loop_capacity(s)) return false;
     const char* env = getenv("BAY_LOOP");
     return !(env && env[0] == '0');
 }
@@ -1009,7 +1098,8 @@ static int move_bare_loop(bay_sampler* s, int64_t n, const float* betas, float c
             s->peer_epoch += 2u * n_steps;
             s->soa_stale = m->mirror;
         }
-        CUresult cr = g_cu.LaunchCooperativeKernel(m->f_loop, cdiv(ke - kb, m->loop_block), 1, 1, m->loop_block, 1, 1, 0,
+        TRY(bind_params(s));
+        CUresult cr = g_cu.LaunchCooperativeKernel(fn_loop(s), cdiv(ke - kb, m->loop_block), 1, 1, m->loop_block, 1, 1, 0,
                                                    reinterpret_cast<CUstream>(e->stream), args.data());
         if (cr != CUDA_SUCCESS) return cu_fail(cr, "cuLaunchCooperativeKernel(bay_stretch_loop)");
         g_launches++;

@@ -316,11 +316,33 @@ def mvn_model(d: int = 100) -> DeviceModel:
 
     params = [mu (d) | U (d x d row-major, upper triangular, zeros below the diagonal)] with Sigma^-1 = U^T U,
     so logpdf = -0.5 * |U (x - mu)|^2.  d must be a multiple of 4: rows of U and the centred point are read as
-    aligned float4 (one 16-byte load per 4 FMAs); only the blocks on or right of the diagonal are visited
-    (~d(d+4)/2 FMAs instead of d^2)."""
+    aligned float4; only the blocks on or right of the diagonal are visited (~d(d+8)/2 FMAs instead of d^2).
+    Eight rows of U at a time: each 4 centred coordinates feed 32 independent ``fmaf`` chains (explicit, so the GPU
+    and the CPU oracle contract the same way)."""
     if d % 4:
         raise ValueError("mvn_model needs a dimension that is a multiple of 4")
     q = d // 4
+
+    def rows_block(nr: int, first_row: str, first_col: str) -> str:
+        accs = ", ".join(f"r{i} = 0.0f" for i in range(nr))
+        loads = "\n".join(f"                const float4 u{i} = U0[{i} * {q} + j];" for i in range(nr))
+        fmas = "\n".join(
+            f"                r{i} = fmaf(u{i}.w, v.w, fmaf(u{i}.z, v.z, fmaf(u{i}.y, v.y, fmaf(u{i}.x, v.x, r{i}))));"
+            for i in range(nr))
+        norm = " + ".join(f"r{i} * r{i}" for i in range(nr))
+        return f"""{{
+            REAL {accs};
+            const float4* U0 = &U[({first_row}) * {q}];
+#pragma unroll 2
+            for (uint32_t j = {first_col}; j < {q}; j++) {{
+                const float4 v = c[j];
+{loads}
+{fmas}
+            }}
+            acc += {norm};
+        }}"""
+
+    full, rest = d // 8, d % 8
     body = f"""
         float4 c[{q}];
         for (uint32_t i = 0; i < {q}; i++) {{
@@ -331,19 +353,8 @@ def mvn_model(d: int = 100) -> DeviceModel:
         }}
         const float4* U = (const float4*)&params[{d}];
         REAL acc = 0.0f;
-        for (uint32_t b = 0; b < {q}; b++) {{      /* four rows of U at a time: each c[j] feeds 16 independent FMAs */
-            REAL r0 = 0.0f, r1 = 0.0f, r2 = 0.0f, r3 = 0.0f;
-            const float4* U0 = &U[(4 * b) * {q}];
-            for (uint32_t j = b; j < {q}; j++) {{
-                const float4 v = c[j];
-                const float4 u0 = U0[j], u1 = U0[{q} + j], u2 = U0[2 * {q} + j], u3 = U0[3 * {q} + j];
-                r0 += (u0.x * v.x + u0.y * v.y) + (u0.z * v.z + u0.w * v.w);
-                r1 += (u1.x * v.x + u1.y * v.y) + (u1.z * v.z + u1.w * v.w);
-                r2 += (u2.x * v.x + u2.y * v.y) + (u2.z * v.z + u2.w * v.w);
-                r3 += (u3.x * v.x + u3.y * v.y) + (u3.z * v.z + u3.w * v.w);
-            }}
-            acc += (r0 * r0 + r1 * r1) + (r2 * r2 + r3 * r3);
-        }}
+        for (uint32_t b = 0; b < {full}; b++) {rows_block(8, "8 * b", "2 * b")}
+        {rows_block(rest, str(8 * full), str(2 * full)) if rest else ""}
         return -0.5f * acc;"""
     src = distribution_source(f"mvn{d}_mcmc_logpdf", body)
     return DeviceModel(f"mvn{d}", (src,), f"mvn{d}_mcmc_logpdf", d, d + d * d,

@@ -407,11 +407,12 @@ VARIANT_CASES = [("gaussian-d1", lambda: (models.GAUSSIAN, f32([3, 1]), f32([-7,
 
 @pytest.mark.parametrize("name,case", VARIANT_CASES, ids=[c[0] for c in VARIANT_CASES])
 def test_persistent_loop_and_mirror_do_not_change_the_chain(factory, name, case, monkeypatch):
-    """The persistent step loop (one cooperative launch for n steps) and the AoS mirror of the ensemble are pure
-    implementation choices: chains must be bit-identical with either switched off (BAY_LOOP=0, BAY_MIRROR=0)."""
+    """The persistent step loop (one cooperative launch for n steps), the AoS mirror of the ensemble and the
+    constant-memory copy of the parameters are pure implementation choices: chains must be bit-identical with any of
+    them switched off (BAY_LOOP=0, BAY_MIRROR=0, BAY_CPARAMS=0)."""
     model, params, limits, walkers = case()
     base = _chain_state(factory, model, params, limits, walkers)
-    for var in ("BAY_LOOP", "BAY_MIRROR"):
+    for var in ("BAY_LOOP", "BAY_MIRROR", "BAY_CPARAMS"):
         monkeypatch.setenv(var, "0")
         other = _chain_state(factory, model, params, limits, walkers)     # the model is recompiled per sampler factory
         monkeypatch.delenv(var)
@@ -419,3 +420,27 @@ def test_persistent_loop_and_mirror_do_not_change_the_chain(factory, name, case,
         assert np.array_equal(base[0]["logfn"], other[0]["logfn"], equal_nan=True), (name, var)
         assert base[1] == other[1], (name, var)
         assert np.array_equal(base[2][0], other[2][0]) and np.array_equal(base[2][1], other[2][1]), (name, var)
+
+
+def test_constant_parameter_block_follows_the_sampler(factory):
+    """Samplers of ONE compiled model share its __constant__ parameter block: interleaving two samplers with
+    different parameters must give each the chain it has alone."""
+    model = models.mvn_model(8)
+    pa, _, _ = models.mvn_params(8, seed=1)
+    pb, _, _ = models.mvn_params(8, seed=2)
+    assert pa.size >= 64 and not np.array_equal(pa, pb)
+    lim = model.limits_array()
+
+    def alone(params):
+        s = factory.mcmc_factory(model).create_sampler(5, 1024, params).init_position(6, lim)
+        s.burn_in(6, 2.0)
+        s.burn_in(5, 2.0)
+        return s.get_state()
+
+    sf = factory.mcmc_factory(model)
+    a = sf.create_sampler(5, 1024, pa).init_position(6, lim)
+    b = sf.create_sampler(5, 1024, pb).init_position(6, lim)
+    a.burn_in(6, 2.0); b.burn_in(6, 2.0); a.burn_in(5, 2.0); b.burn_in(5, 2.0)
+    for got, want in ((a.get_state(), alone(pa)), (b.get_state(), alone(pb))):
+        assert np.array_equal(got["xs"], want["xs"]) and np.array_equal(got["logfn"], want["logfn"])
+    assert sf.kernel_info("bay_stretch_bare")["registers"] > 0
