@@ -245,7 +245,8 @@ struct bay_sampler;
 struct bay_model {
     bay_engine* e = nullptr;
     CUmodule mod = nullptr;
-    CUfunction f_bare = nullptr, f_accu = nullptr, f_logfn = nullptr, f_loop = nullptr;
+    CUfunction f_bare = nullptr, f_accu = nullptr, f_logfn = nullptr, f_loop = nullptr, f_accu_loop = nullptr;
+    int accu_loop_capacity = 0;   // co-resident CTAs (WGS threads) of the persistent run-sampler! kernel
     int loop_capacity = 0;   // co-resident CTAs of the persistent step-loop kernel on this device
     int loop_block = 128;    // its CTA size
     // GLM (row-additive Bernoulli-logit) path, present iff `glm`
@@ -256,8 +257,8 @@ struct bay_model {
     // Constant-parameter variant (stretch_program.inc, BAY_CPARAMS): the same program compiled with the parameter
     // vector in __constant__ memory; built on demand for samplers whose parameters fit (cparams_try)
     CUmodule cmod = nullptr;
-    CUfunction c_bare = nullptr, c_accu = nullptr, c_logfn = nullptr, c_loop = nullptr;
-    int c_loop_capacity = 0;
+    CUfunction c_bare = nullptr, c_accu = nullptr, c_logfn = nullptr, c_loop = nullptr, c_accu_loop = nullptr;
+    int c_loop_capacity = 0, c_accu_loop_capacity = 0;
     int cvar_state = 0;                       // 0 not tried, 1 built, -1 unavailable
     CUdeviceptr cparams = 0;
     const bay_sampler* cparams_owner = nullptr;   // whose parameters the constant block holds right now
@@ -559,7 +560,7 @@ extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsr
     }
     struct { const char* name; CUfunction* f; } fns[] = {
         {"bay_stretch_bare", &m->f_bare}, {"bay_stretch_accu", &m->f_accu}, {"bay_logfn", &m->f_logfn},
-        {"bay_stretch_loop", &m->f_loop}};
+        {"bay_stretch_loop", &m->f_loop}, {"bay_stretch_accu_loop", &m->f_accu_loop}};
     for (auto& fn : fns) {
         cr = g_cu.ModuleGetFunction(fn.f, m->mod, fn.name);
         if (cr != CUDA_SUCCESS) {
@@ -573,6 +574,8 @@ extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsr
         m->loop_block = loop_block_for(dim, m->block);
         if (g_cu.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, m->f_loop, m->loop_block, 0) == CUDA_SUCCESS)
             m->loop_capacity = per_sm * e->sm_count;
+        if (g_cu.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, m->f_accu_loop, e->wgs, 0) == CUDA_SUCCESS)
+            m->accu_loop_capacity = per_sm * e->sm_count;
     }
     if ((flags & BAY_MODEL_GLM_LOGISTIC) && dim % 4 == 0) {
         struct { const char* name; CUfunction* f; } gfns[] = {
@@ -638,12 +641,15 @@ static void cparams_try(bay_sampler* s, int64_t params_count) {
                   g_cu.ModuleGetFunction(&m->c_accu, m->cmod, "bay_stretch_accu") == CUDA_SUCCESS &&
                   g_cu.ModuleGetFunction(&m->c_logfn, m->cmod, "bay_logfn") == CUDA_SUCCESS &&
                   g_cu.ModuleGetFunction(&m->c_loop, m->cmod, "bay_stretch_loop") == CUDA_SUCCESS &&
+                  g_cu.ModuleGetFunction(&m->c_accu_loop, m->cmod, "bay_stretch_accu_loop") == CUDA_SUCCESS &&
                   g_cu.ModuleGetGlobal(&m->cparams, &bytes, m->cmod, "bay_cparams") == CUDA_SUCCESS &&
                   bytes >= sizeof(float) * kCparamsCap;
         if (!ok) { g_cu.ModuleUnload(m->cmod); m->cmod = nullptr; return; }
         int per_sm = 0;
         if (g_cu.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, m->c_loop, m->loop_block, 0) == CUDA_SUCCESS)
             m->c_loop_capacity = per_sm * m->e->sm_count;
+        if (g_cu.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, m->c_accu_loop, m->e->wgs, 0) == CUDA_SUCCESS)
+            m->c_accu_loop_capacity = per_sm * m->e->sm_count;
         m->cvar_state = 1;
     }
     s->cp = m->cvar_state == 1;
@@ -654,6 +660,10 @@ static CUfunction fn_accu(const bay_sampler* s) { return s->cp ? s->m->c_accu : 
 static CUfunction fn_logfn(const bay_sampler* s) { return s->cp ? s->m->c_logfn : s->m->f_logfn; }
 static CUfunction fn_loop(const bay_sampler* s) { return s->cp ? s->m->c_loop : s->m->f_loop; }
 static int loop_capacity(const bay_sampler* s) { return s->cp ? s->m->c_loop_capacity : s->m->loop_capacity; }
+static CUfunction fn_accu_loop(const bay_sampler* s) { return s->cp ? s->m->c_accu_loop : s->m->f_accu_loop; }
+static int accu_loop_capacity(const bay_sampler* s) {
+    return s->cp ? s->m->c_accu_loop_capacity : s->m->accu_loop_capacity;
+}
 
 // The constant block belongs to the module, i.e. to all samplers of the model: (re)load it when another sampler's
 // parameters are in it.  Stream-ordered, so kernels already queued keep the values they were launched with.
@@ -777,7 +787,7 @@ static int sampler_alloc(bay_sampler* s) {
     CK(cudaMalloc(&s->loop_bar, sizeof(unsigned int) * 2));
     CK(cudaMemsetAsync(s->loop_bar, 0, sizeof(unsigned int) * 2, e->stream));
     CK(cudaMalloc(&s->accept, sizeof(uint32_t) * s->G));
-    CK(cudaMalloc(&s->blk_sums, sizeof(float) * D * s->G));
+    CK(cudaMalloc(&s->blk_sums, sizeof(float) * 2 * D * s->G));   // second half: scratch of the run-sampler! loop
     CK(cudaMalloc(&s->accept_total, sizeof(unsigned long long)));
     CK(cudaMalloc(&s->hist_counts, sizeof(uint32_t) * wgs * D));
     CK(cudaMalloc(&s->mm, sizeof(uint32_t) * 2 * D));
@@ -789,7 +799,7 @@ static int sampler_alloc(bay_sampler* s) {
     CK(cudaMemsetAsync(s->xs, 0, sizeof(float) * D * W, e->stream));
     CK(cudaMemsetAsync(s->lp, 0, sizeof(float) * W, e->stream));
     CK(cudaMemsetAsync(s->accept, 0, sizeof(uint32_t) * s->G, e->stream));
-    CK(cudaMemsetAsync(s->blk_sums, 0, sizeof(float) * D * s->G, e->stream));
+    CK(cudaMemsetAsync(s->blk_sums, 0, sizeof(float) * 2 * D * s->G, e->stream));
     CK(cudaMemsetAsync(s->hist_counts, 0, sizeof(uint32_t) * wgs * D, e->stream));
     return BAY_OK;
 }
@@ -1228,6 +1238,38 @@ extern "C" int bay_move(bay_sampler* s) {
     CKLAUNCH();
     s->means_n++;
     s->move_counter++;
+    return BAY_OK;
+}
+
+// n x move! in one cooperative launch (bay_stretch_accu_loop) when the half-ensemble's blocks are co-resident.
+static bool accu_loop_usable(const bay_sampler* s, int64_t n) {
+    const bay_model* m = s->m;
+    if (m->glm || !fn_accu_loop(s) || n < 2 || partitioned(s)) return false;
+    if ((int64_t)s->G > accu_loop_capacity(s)) return false;
+    const char* env = getenv("BAY_LOOP");
+    return !(env && env[0] == '0');
+}
+
+static int move_accu_loop(bay_sampler* s, int64_t n) {
+    bay_model* m = s->m;
+    bay_engine* e = m->e;
+    float cA, cB, cC;
+    stretch_coeffs(s->a_move, &cA, &cB, &cC);
+    TRY(ensure_means(s, s->means_n + n));
+    TRY(bind_params(s));
+    uint32_t K = (uint32_t)s->H, pitch = (uint32_t)s->W, seed = (uint32_t)s->move_seed, step0 = s->move_counter;
+    uint32_t n_steps = (uint32_t)n;
+    float factor = 0.5f / ((float)e->wgs * (float)s->G);
+    float* means = s->means + (size_t)s->means_n * s->D;
+    std::vector<void*> args = {&K, &seed, &s->data_len, &s->params_len, &s->params, &s->xs, &pitch, &s->lp, &s->accept,
+                               &s->blk_sums, &cA, &cB, &cC, &step0, &n_steps, &s->loop_bar, &means, &factor};
+    if (m->mirror) args.push_back(&s->xa);
+    CUresult cr = g_cu.LaunchCooperativeKernel(fn_accu_loop(s), s->G, 1, 1, (unsigned)e->wgs, 1, 1, 0,
+                                               reinterpret_cast<CUstream>(e->stream), args.data());
+    if (cr != CUDA_SUCCESS) return cu_fail(cr, "cuLaunchCooperativeKernel(bay_stretch_accu_loop)");
+    g_launches++;
+    s->means_n += n;
+    s->move_counter += (uint32_t)n;
     return BAY_OK;
 }
 

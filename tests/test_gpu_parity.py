@@ -394,8 +394,8 @@ def _chain_state(factory, model, params, limits, walkers):
     s.anneal(mcmc.minus_n(7.0), 7, 2.2)
     s.sample(walkers)                      # one more bare move
     st = s.get_state()
-    r = s.run_sampler(64, 2.0)
-    return st, r["acceptance-rate"], s.accu_blocks()
+    r = s.run_sampler(65, 2.0)             # odd: exercises the double-buffered block sums of the run-sampler! loop
+    return st, r["acceptance-rate"], s.accu_blocks(), s.last_means(65), r["autocorrelation"].tau, s.get_state()
 
 
 VARIANT_CASES = [("gaussian-d1", lambda: (models.GAUSSIAN, f32([3, 1]), f32([-7, 7]), 4096)),
@@ -420,6 +420,9 @@ def test_persistent_loop_and_mirror_do_not_change_the_chain(factory, name, case,
         assert np.array_equal(base[0]["logfn"], other[0]["logfn"], equal_nan=True), (name, var)
         assert base[1] == other[1], (name, var)
         assert np.array_equal(base[2][0], other[2][0]) and np.array_equal(base[2][1], other[2][1]), (name, var)
+        assert np.array_equal(base[3], other[3]), (name, var)                      # per-step ensemble means
+        assert np.array_equal(base[4], other[4], equal_nan=True), (name, var)      # autocorrelation times
+        assert np.array_equal(base[5]["xs"], other[5]["xs"]), (name, var)          # state after run-sampler!
 
 
 def test_constant_parameter_block_follows_the_sampler(factory):
