@@ -96,6 +96,18 @@ def algorithmic_bytes_per_walker_step(dim: int, p_acc: float) -> float:
     return 4.0 * (2 * dim + 1) + 4.0 * (dim + 1) * p_acc
 
 
+def ncu_traffic(key: str, kernel: str) -> dict:
+    """roofline.traffic: DRAM bytes per launch of the dominant kernel, measured once under `ncu --set full`
+    (profiles/ncu_traffic.json names the capture); None when no capture of this workload's kernel is committed."""
+    try:
+        entry = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text()).get(key)
+    except (OSError, ValueError):
+        entry = None
+    if not entry or entry.get("kernel") != kernel:
+        return {"traffic": None}
+    return {"traffic": entry["bytes"], "traffic_source": entry["source"]}
+
+
 # --------------------------------------------------------------------------------------------- clocks --
 class ClockSampler(threading.Thread):
     """Samples SM clock and clock-event reasons through NVML every 20 ms while the timed region runs."""
@@ -366,8 +378,13 @@ def main():
         peak = float(peaks["bf16_tflops_sustained"]) if peaks else 1400.0
         achieved = flops_per_launch / (per_launch_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": kernel_name, "peak_source": peak_src, "flops_per_launch": flops_per_launch,
+                **ncu_traffic(wl["key"], kernel_name), "kernel": kernel_name, "peak_source": peak_src,
+                "flops_per_launch": flops_per_launch,
                 "launch_us": per_launch_ms * 1e3,
+                "executed_mma_tflops": 3.0 * achieved,
+                "note": "achieved counts ALGORITHMIC flops (2*rows*D per walker); fp32-level accuracy from bf16 inputs "
+                        "takes a 3-term split, so the tensor pipe executes 3x that and frac cannot exceed 1/3; the "
+                        "kernel's binding unit is MUFU (one ex2 per row x walker), see DESIGN.md 4.2",
                 "hbm_view": {"bytes_per_launch": flops_per_launch / min(W // 2, 512) * 2.0,
                              "achieved_GBps": flops_per_launch / min(W // 2, 512) * 2.0 / (per_launch_ms * 1e-3) / 1e9,
                              "note": "dataset bytes (bf16 hi+lo planes = 4 B/element) streamed once per launch"}}
@@ -377,7 +394,8 @@ def main():
         peak = float(peaks["hbm_gbs"]) if peaks else 6650.0
         achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": kernel_name, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch,
+                **ncu_traffic(wl["key"], kernel_name), "kernel": kernel_name, "peak_source": peak_src,
+                "bytes_per_launch": bytes_per_launch,
                 "launch_us": per_launch_ms * 1e3}
 
     if rank == 0:
