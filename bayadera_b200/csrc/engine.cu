@@ -320,6 +320,7 @@ struct bay_sampler {
     uint32_t glm_chunks = 0, glm_rows_per_chunk = 0;
     // tensor-core variant (DIM <= 64): bf16 hi/lo planes of the dataset and of the walker block + TMA maps
     bool glm_tc = false;
+    uint32_t glm_nkc = 1;                     // 64-wide K chunks per row (DIM <= 64: 1, <= 128: 2)
     __nv_bfloat16 *glm_xh = nullptr, *glm_xl = nullptr, *glm_ah = nullptr, *glm_al = nullptr;
     CUtensorMap glm_map_xh, glm_map_xl;
     std::map<uint64_t, std::pair<CUtensorMap, CUtensorMap>> glm_amaps;   // (first walker, count) -> (hi, lo) maps

@@ -26,7 +26,8 @@ namespace bay {
 namespace tc {
 
 constexpr int TILE = 128;                       // MMA M (walkers per block) and N (rows per tile)
-constexpr int KD = 64;                          // model dimension handled by this kernel
+constexpr int KD = 64;                          // K extent of one operand tile (128 B of bf16 = one swizzle row)
+constexpr int MAX_KC = 2;                       // K chunks per dataset row: model dimension <= 128
 constexpr int NSTAGE = 3;                       // X-tile ring
 constexpr int NACC = 4;                         // TMEM accumulator stages (4 x 128 columns = 512)
 constexpr int MAX_WB = 4;                       // walker blocks per launch (512 walkers)
@@ -36,8 +37,8 @@ constexpr int THREADS = (4 * NGRP + 2) * 32;    // 16 epilogue warps + TMA warp 
 constexpr uint32_t IDESC =                      // kind::f16: D=f32, A=B=bf16, both K-major, N=128, M=128
     (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
 
-__host__ __device__ constexpr size_t smem_bytes(int nwb) {
-    return 1024 /*alignment slack*/ + (size_t)nwb * 2 * TILE_BYTES + (size_t)NSTAGE * 2 * TILE_BYTES + 256;
+__host__ __device__ constexpr size_t smem_bytes(int nwb, int nkc) {
+    return 1024 /*alignment slack*/ + (size_t)nwb * nkc * 2 * TILE_BYTES + (size_t)NSTAGE * 2 * TILE_BYTES + 256;
 }
 
 // ------------------------------------------------------------------ PTX helpers --
@@ -118,19 +119,21 @@ __device__ __forceinline__ float lg2_approx(float x) {
         : "r"(taddr) : "memory")
 
 // ------------------------------------------------------------------ the kernel --
-// map_xh/map_xl: [rows][64] bf16 planes of the dataset; map_ah/map_al: [n_walkers][64] bf16 planes of the
+// map_xh/map_xl: [rows][64*NKC] bf16 planes of the dataset; map_ah/map_al: [n_walkers][64*NKC] bf16 planes of the
 // walker block (hi, lo), origin at the first walker of this launch.  partial: [NGRP*gridDim.x][ldp] doubles;
 // entry (NGRP*cta + group, wb*128 + lane) = that epilogue thread's sum.
-template <int NWB>
-__global__ void __launch_bounds__(THREADS, 1)  // NWB in {1, 2, 4}
+// NKC = 2 (64 < DIM <= 128): a row tile arrives as two 64-wide K chunks, each its own ring stage, and the MMAs of
+// both accumulate into the same TMEM stage; the walker block then takes 64 KB per 128 walkers, so NWB <= 2.
+template <int NWB, int NKC>
+__global__ void __launch_bounds__(THREADS, 1)  // (NWB, NKC) in {1, 2, 4} x {1}, {1, 2} x {2}
 k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                 const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                 const uint32_t rows, const uint32_t n_tiles, double* __restrict__ partial, const uint32_t ldp) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* a_hi = smem;                                   // NWB tiles
-    uint8_t* a_lo = a_hi + NWB * TILE_BYTES;                // NWB tiles
-    uint8_t* b_base = a_lo + NWB * TILE_BYTES;              // NSTAGE x (hi, lo)
+    uint8_t* a_hi = smem;                                   // NWB x NKC tiles, tile (wb, kc) at wb*NKC + kc
+    uint8_t* a_lo = a_hi + NWB * NKC * TILE_BYTES;          // NWB x NKC tiles
+    uint8_t* b_base = a_lo + NWB * NKC * TILE_BYTES;        // NSTAGE x (hi, lo)
     uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + NSTAGE * 2 * TILE_BYTES);
     uint64_t* full_bar = bars;                              // [NSTAGE] TMA -> MMA
     uint64_t* empty_bar = bars + NSTAGE;                    // [NSTAGE] MMA -> TMA
@@ -160,18 +163,21 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     if (warp == 4 * NGRP) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            mbar_expect_tx(a_bar, NWB * 2 * TILE_BYTES);
-            for (int wb = 0; wb < NWB; wb++) {
-                tma_load_2d(a_hi + wb * TILE_BYTES, &map_ah, 0, wb * TILE, a_bar);
-                tma_load_2d(a_lo + wb * TILE_BYTES, &map_al, 0, wb * TILE, a_bar);
-            }
+            mbar_expect_tx(a_bar, NWB * NKC * 2 * TILE_BYTES);
+            for (int wb = 0; wb < NWB; wb++)
+                for (int kc = 0; kc < NKC; kc++) {
+                    tma_load_2d(a_hi + (wb * NKC + kc) * TILE_BYTES, &map_ah, kc * KD, wb * TILE, a_bar);
+                    tma_load_2d(a_lo + (wb * NKC + kc) * TILE_BYTES, &map_al, kc * KD, wb * TILE, a_bar);
+                }
             for (uint32_t it = 0; it < my_tiles; it++) {
-                const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                mbar_expect_tx(&full_bar[s], 2 * TILE_BYTES);
                 const int row0 = (int)((blockIdx.x + it * gridDim.x) * TILE);
-                tma_load_2d(b_base + (2 * s) * TILE_BYTES, &map_xh, 0, row0, &full_bar[s]);
-                tma_load_2d(b_base + (2 * s + 1) * TILE_BYTES, &map_xl, 0, row0, &full_bar[s]);
+                for (uint32_t kc = 0; kc < NKC; kc++) {
+                    const uint32_t st = it * NKC + kc, s = st % NSTAGE, ph = (st / NSTAGE) & 1u;
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    mbar_expect_tx(&full_bar[s], 2 * TILE_BYTES);
+                    tma_load_2d(b_base + (2 * s) * TILE_BYTES, &map_xh, (int)(kc * KD), row0, &full_bar[s]);
+                    tma_load_2d(b_base + (2 * s + 1) * TILE_BYTES, &map_xl, (int)(kc * KD), row0, &full_bar[s]);
+                }
             }
         }
     } else if (warp == 4 * NGRP + 1) {
@@ -180,28 +186,38 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
             mbar_wait(a_bar, 0);
             uint32_t item = 0;
             for (uint32_t it = 0; it < my_tiles; it++) {
-                const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
-                mbar_wait(&full_bar[s], ph);
+                uint32_t stage[NKC];
+                uint64_t bh[NKC], bl[NKC];
+#pragma unroll
+                for (int kc = 0; kc < NKC; kc++) {          // all K chunks of the row tile must have landed
+                    const uint32_t st = it * NKC + kc, s = st % NSTAGE, ph = (st / NSTAGE) & 1u;
+                    mbar_wait(&full_bar[s], ph);
+                    stage[kc] = s;
+                    bh[kc] = make_desc(smem_u32(b_base + (2 * s) * TILE_BYTES));
+                    bl[kc] = make_desc(smem_u32(b_base + (2 * s + 1) * TILE_BYTES));
+                }
                 tc_fence_after();
-                const uint64_t bh = make_desc(smem_u32(b_base + (2 * s) * TILE_BYTES));
-                const uint64_t bl = make_desc(smem_u32(b_base + (2 * s + 1) * TILE_BYTES));
 #pragma unroll
                 for (int wb = 0; wb < NWB; wb++, item++) {
                     const uint32_t a = item % NACC, aph = (item / NACC) & 1u;
                     mbar_wait(&tempty_bar[a], aph ^ 1u);
                     tc_fence_after();
                     const uint32_t d = tmem_base + a * TILE;
-                    const uint64_t ah = make_desc(smem_u32(a_hi + wb * TILE_BYTES));
-                    const uint64_t al = make_desc(smem_u32(a_lo + wb * TILE_BYTES));
 #pragma unroll
-                    for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, ah + 2 * k, bh + 2 * k, k > 0);   // hi*hi
+                    for (int kc = 0; kc < NKC; kc++) {
+                        const uint64_t ah = make_desc(smem_u32(a_hi + (wb * NKC + kc) * TILE_BYTES));
+                        const uint64_t al = make_desc(smem_u32(a_lo + (wb * NKC + kc) * TILE_BYTES));
 #pragma unroll
-                    for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, ah + 2 * k, bl + 2 * k, 1);       // hi*lo
+                        for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, ah + 2 * k, bh[kc] + 2 * k, kc > 0 || k > 0);   // hi*hi
 #pragma unroll
-                    for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, al + 2 * k, bh + 2 * k, 1);       // lo*hi
+                        for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, ah + 2 * k, bl[kc] + 2 * k, 1);                 // hi*lo
+#pragma unroll
+                        for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, al + 2 * k, bh[kc] + 2 * k, 1);                 // lo*hi
+                    }
                     tc_commit(&tfull_bar[a]);
                 }
-                tc_commit(&empty_bar[s]);   // the X tile is free once all MMAs that read it completed
+#pragma unroll
+                for (int kc = 0; kc < NKC; kc++) tc_commit(&empty_bar[stage[kc]]);   // chunks free once their MMAs completed
             }
         }
     } else {
@@ -283,13 +299,14 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
 
 constexpr float LOG2E = 1.4426950408889634f;
 
-// points (SoA, dim 64 x n, pitch) -> bf16 hi/lo planes [n][64] (row = walker) of theta * log2(e), the A operand
+// points (SoA, dim x n, pitch) -> bf16 hi/lo planes [n][kdp] (row = walker; kdp = 64 or 128) of theta * log2(e), the
+// A operand
 __global__ void k_glm_split_points(const float* __restrict__ pts, uint32_t pitch, uint32_t n, uint32_t dim,
-                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;    // e = k*64 + i, coalesced stores
-    if (e >= n * KD) return;
-    const uint32_t k = e / KD, i = e % KD;
-    // dim < 64: the K extent is zero-padded (the MMA cost is hidden under the MUFU-bound epilogue anyway)
+                                   uint32_t kdp, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;    // e = k*kdp + i, coalesced stores
+    if (e >= n * kdp) return;
+    const uint32_t k = e / kdp, i = e % kdp;
+    // dim < kdp: the K extent is zero-padded (the MMA cost is hidden under the MUFU-bound epilogue anyway)
     const float x = i < dim ? __fmul_rn(pts[(size_t)i * pitch + k], LOG2E) : 0.0f;
     const __nv_bfloat16 h = __float2bfloat16_rn(x);
     hi[e] = h;
@@ -313,14 +330,14 @@ __global__ void k_glm_finish_tc(uint32_t n, uint32_t chunks, uint32_t ldp, const
     if (lane == 0) sp[k] = s;
 }
 
-// dataset rows [y, x_1..x_dim] (stride dim + 1) -> bf16 hi/lo planes [rows][64], zero-padded past dim
-__global__ void k_glm_split_rows(const float* __restrict__ data, uint64_t rows, uint32_t dim,
+// dataset rows [y, x_1..x_dim] (stride dim + 1) -> bf16 hi/lo planes [rows][kdp], zero-padded past dim
+__global__ void k_glm_split_rows(const float* __restrict__ data, uint64_t rows, uint32_t dim, uint32_t kdp,
                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-    const uint64_t total = rows * KD;
+    const uint64_t total = rows * kdp;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        const uint64_t r = e / KD;
-        const uint32_t i = (uint32_t)(e % KD);
+        const uint64_t r = e / kdp;
+        const uint32_t i = (uint32_t)(e % kdp);
         const float x = i < dim ? data[r * (dim + 1) + 1 + i] : 0.0f;
         const __nv_bfloat16 h = __float2bfloat16_rn(x);
         hi[e] = h;
