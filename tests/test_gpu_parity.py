@@ -447,3 +447,32 @@ def test_constant_parameter_block_follows_the_sampler(factory):
     for got, want in ((a.get_state(), alone(pa)), (b.get_state(), alone(pb))):
         assert np.array_equal(got["xs"], want["xs"]) and np.array_equal(got["logfn"], want["logfn"])
     assert sf.kernel_info("bay_stretch_bare")["registers"] > 0
+
+
+def test_large_ensemble_bit_exact_and_index_arithmetic(factory):
+    """Maximum-size edge: 2^24 walkers (the persistent loop does not fit, grids of 32 768 CTAs, 64 MB state) must
+    still follow the oracle bit for bit, and a 2^21 x 12-D ensemble (offsets beyond 2^24 elements per half) must
+    keep exact moments bookkeeping."""
+    walkers = 1 << 24
+    _, gpu, cpu = make_pair(factory, models.UNIFORM, 77, walkers, f32([-1, 2]), f32([-1, 2]))
+    for s in (gpu, cpu):
+        s.burn_in(2, 2.0)
+    st = gpu.get_state()
+    assert np.array_equal(st["xs"].reshape(-1), cpu.xs)
+    assert logpdf_close(st["logfn"], cpu.lp).all()          # fast-math log on the device
+    h = gpu.histogram(1)
+    counts = gpu.histogram_counts()
+    assert int(counts.sum()) == walkers
+    limits = orc.min_max(cpu.xs.reshape(walkers, 1), 1, walkers)
+    assert np.array_equal(h.limits.reshape(-1), limits)
+    assert np.array_equal(counts.reshape(-1), orc.histogram_counts(cpu.xs.reshape(walkers, 1), 1, walkers, G.WGS, limits))
+    del gpu, cpu
+
+    d, walkers = 12, 1 << 21
+    model = models.mvn_model(d)
+    params, mu, _ = models.mvn_params(d)
+    s = factory.mcmc_factory(model).create_sampler(3, walkers, params).init_position(4, model.limits_array())
+    s.burn_in(3, 2.0)
+    x = s.sample(walkers)
+    assert x.shape == (walkers, d) and np.isfinite(x).all()
+    assert np.allclose(s.mean(), x.astype(np.float64).mean(axis=0), rtol=0, atol=2e-4)
