@@ -252,6 +252,9 @@ def main():
     ap.add_argument("--walkers", type=int, default=0)
     ap.add_argument("--wgs", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="walker-partitioned workloads: keep the config's TOTAL ensemble and split it over the GPUs "
+                         "(default: the config's ensemble per GPU, weak scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -313,6 +316,8 @@ def main():
             local_rows, seed = wl["rows"], 2024
         params = bb.DeviceParams.from_torch(logreg_rows_device(torch, local_rows, D, seed, torch.device("cuda", local_rank)))
     # every rank drives the same (replicated or partitioned) ensemble: identical seeds everywhere
+    if partition and args.strong:
+        W = max(W // world // (2 * args.wgs), 1) * 2 * args.wgs     # this GPU's share of the config's ensemble
     W_global = W * world if partition else W
     sampler = sfactory.create_sampler(123, W_global, params)
     sampler.init_position(1000, wl["limits"])
@@ -412,7 +417,7 @@ def main():
             info = sfactory.kernel_info(kernel_name)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-                "scaling": "strong" if wl.get("glm") else "weak", "vs_baseline": None,
+                "scaling": "strong" if (wl.get("glm") or args.strong) else "weak", "vs_baseline": None,
                 "dtype": "f32 (bf16x3 split on tensor cores, fp32 accumulate)" if wl.get("glm") else "f32",
                 "data": "synthetic",
                 "config": {"workload": wl["desc"], "walkers_per_gpu": W, "dim": D, "moves_per_step": M, "a": a,
