@@ -229,6 +229,8 @@ inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b
 
 }  // namespace
 
+#define BAY_GLM_ANY (BAY_MODEL_GLM_LOGISTIC | BAY_MODEL_GLM_POISSON)
+
 // ----------------------------------------------------------------- handles --
 struct bay_engine {
     int device = 0;
@@ -252,6 +254,7 @@ struct bay_model {
     // GLM (row-additive Bernoulli-logit) path, present iff `glm`
     CUfunction f_glm_propose = nullptr, f_glm_loglik = nullptr, f_glm_lp_init = nullptr, f_glm_accept = nullptr;
     bool glm = false;
+    int glm_link = 0;      // 0 Bernoulli-logit (softplus), 1 Poisson-log (exp)
     bool mirror = false;   // AoS mirror of the ensemble for the partner gather (DIM >= 4, non-GLM)
     bool peers = false;    // kernels store accepted walkers into every rank's ensemble block (multi-GPU mode A)
     // Constant-parameter variant (stretch_program.inc, BAY_CPARAMS): the same program compiled with the parameter
@@ -432,7 +435,7 @@ static bool engine_wants_peers(const bay_engine* e) {
 // BAY_MIRROR=0 in the environment disables it (A/B measurements).
 static bool model_wants_mirror(int dim, uint32_t flags) {
     if (dim < 4) return false;
-    if ((flags & BAY_MODEL_GLM_LOGISTIC) && dim % 4 == 0) return false;
+    if ((flags & BAY_GLM_ANY) && dim % 4 == 0) return false;
     const char* env = getenv("BAY_MIRROR");
     return !(env && env[0] == '0');
 }
@@ -458,7 +461,7 @@ static int nvrtc_build(const char* const* srcs, int nsrc, const char* logfn_name
         src += "\n";
     }
     src += kStretchProgram;
-    if ((flags & BAY_MODEL_GLM_LOGISTIC) && dim % 4 == 0) src += kGlmProgram;
+    if ((flags & BAY_GLM_ANY) && dim % 4 == 0) src += kGlmProgram;
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-default-device", "-lineinfo", "--std=c++17",
                                      "-DREAL=float", "-DREAL2=float2", "-DACCUMULATOR=float",
                                      "-DLOGFN=" + std::string(logfn_name), "-DDIM=" + std::to_string(dim),
@@ -469,6 +472,7 @@ static int nvrtc_build(const char* const* srcs, int nsrc, const char* logfn_name
         opts.push_back("-DBAY_DIMA=" + std::to_string((dim + 3) / 4 * 4));
     }
     if (peers) opts.push_back("-DBAY_PEERS=1");
+    if (flags & BAY_MODEL_GLM_POISSON) opts.push_back("-DBAY_GLM_LINK=1");
     if (cparams > 0) opts.push_back("-DBAY_CPARAMS=" + std::to_string(cparams));
     // ensemble traffic policy (stretch_program.inc, BAY_STREAM): large-DIM models keep a per-thread local array and
     // their parameter block in L1, which the once-touched ensemble data would otherwise evict
@@ -538,7 +542,7 @@ extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsr
     TRY(use_device(e));
     TRY(load_driver());
     std::vector<char> cubin;
-    const bool glm_model = (flags & BAY_MODEL_GLM_LOGISTIC) && dim % 4 == 0;
+    const bool glm_model = (flags & BAY_GLM_ANY) && dim % 4 == 0;
     const bool peers = engine_wants_peers(e) && !glm_model;
     TRY(nvrtc_build(srcs, nsrc, logfn_name, dim, e->wgs, bare_block_for(dim), flags, peers, false, &cubin, nullptr));
 
@@ -578,7 +582,7 @@ extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsr
         if (g_cu.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, m->f_accu_loop, e->wgs, 0) == CUDA_SUCCESS)
             m->accu_loop_capacity = per_sm * e->sm_count;
     }
-    if ((flags & BAY_MODEL_GLM_LOGISTIC) && dim % 4 == 0) {
+    if ((flags & BAY_GLM_ANY) && dim % 4 == 0) {
         struct { const char* name; CUfunction* f; } gfns[] = {
             {"bay_glm_propose", &m->f_glm_propose}, {"bay_glm_loglik", &m->f_glm_loglik},
             {"bay_glm_lp_init", &m->f_glm_lp_init}, {"bay_glm_accept", &m->f_glm_accept}};
@@ -591,6 +595,7 @@ extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsr
             }
         }
         m->glm = true;
+        m->glm_link = (flags & BAY_MODEL_GLM_POISSON) ? 1 : 0;
     }
     *out = m;
     return BAY_OK;

@@ -124,7 +124,9 @@ __device__ __forceinline__ float lg2_approx(float x) {
 // entry (NGRP*cta + group, wb*128 + lane) = that epilogue thread's sum.
 // NKC = 2 (64 < DIM <= 128): a row tile arrives as two 64-wide K chunks, each its own ring stage, and the MMAs of
 // both accumulate into the same TMEM stage; the walker block then takes 64 KB per 128 walkers, so NWB <= 2.
-template <int NWB, int NKC>
+// LINK = 0: A(eta) = softplus(eta) (Bernoulli-logit); LINK = 1: A(eta) = exp(eta) (Poisson-log): one MUFU.EX2 and one
+// FADD per element, nothing analytic left for the finish kernel.
+template <int NWB, int NKC, int LINK>
 __global__ void __launch_bounds__(THREADS, 1)  // (NWB, NKC) in {1, 2, 4} x {1}, {1, 2} x {2}
 k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                 const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
@@ -250,11 +252,16 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
             auto reduce = [&](const uint32_t (&r)[16]) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
-                    const float e0 = fabsf(__uint_as_float(r[j])), e1 = fabsf(__uint_as_float(r[j + 1]));
-                    const float e2 = fabsf(__uint_as_float(r[j + 2])), e3 = fabsf(__uint_as_float(r[j + 3]));
-                    const float t0 = ex2_approx(-e0), t1 = ex2_approx(-e1), t2 = ex2_approx(-e2), t3 = ex2_approx(-e3);
-                    p0 = fmaf(p0, t0, p0); p1 = fmaf(p1, t1, p1); p2 = fmaf(p2, t2, p2); p3 = fmaf(p3, t3, p3);
-                    m0 += e0; m1 += e1; m2 += e2; m3 += e3;
+                    if (LINK == 1) {   // sum of 2^a = exp(eta)
+                        m0 += ex2_approx(__uint_as_float(r[j])); m1 += ex2_approx(__uint_as_float(r[j + 1]));
+                        m2 += ex2_approx(__uint_as_float(r[j + 2])); m3 += ex2_approx(__uint_as_float(r[j + 3]));
+                    } else {
+                        const float e0 = fabsf(__uint_as_float(r[j])), e1 = fabsf(__uint_as_float(r[j + 1]));
+                        const float e2 = fabsf(__uint_as_float(r[j + 2])), e3 = fabsf(__uint_as_float(r[j + 3]));
+                        const float t0 = ex2_approx(-e0), t1 = ex2_approx(-e1), t2 = ex2_approx(-e2), t3 = ex2_approx(-e3);
+                        p0 = fmaf(p0, t0, p0); p1 = fmaf(p1, t1, p1); p2 = fmaf(p2, t2, p2); p3 = fmaf(p3, t3, p3);
+                        m0 += e0; m1 += e1; m2 += e2; m3 += e3;
+                    }
                 }
             };
             BAY_TMEM_LD16(ra, tbase);
@@ -276,14 +283,20 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                 if (c + 32 < TILE) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             }
             // each chain holds 32 factors <= 2.  item value (in units of ln2): sum log2(1+t) + sum|a|/2
-            const float lg = (lg2_approx(p0 * p1) + lg2_approx(p2 * p3)) - (float)(TILE - valid);
-            const float x = fmaf(0.5f, (m0 + m1) + (m2 + m3), lg);
+            // zero-filled rows past the end of the dataset contribute exactly 1 each (2^0, or one factor 2)
+            float x;
+            if (LINK == 1) {
+                x = ((m0 + m1) + (m2 + m3)) - (float)(TILE - valid);
+            } else {
+                const float lg = (lg2_approx(p0 * p1) + lg2_approx(p2 * p3)) - (float)(TILE - valid);
+                x = fmaf(0.5f, (m0 + m1) + (m2 + m3), lg);
+            }
             const float s = hi + x;                      // Knuth two-sum: (hi, lo) += x without fp64 (DADD is slow here)
             const float bp = s - hi;
             lo += (hi - (s - bp)) + (x - bp);
             hi = s;
         }
-        const double acc64 = ((double)hi + (double)lo) * 0.6931471805599453;
+        const double acc64 = ((double)hi + (double)lo) * (LINK == 1 ? 1.0 : 0.6931471805599453);
         const size_t base = (size_t)(NGRP * blockIdx.x + grp) * ldp + quarter * 32 + lane;
 #pragma unroll
         for (int wb = 0; wb < NWB; wb++) partial[base + wb * TILE] = (wb == (int)wb_mine) ? acc64 : 0.0;
@@ -318,13 +331,14 @@ __global__ void k_glm_split_points(const float* __restrict__ pts, uint32_t pitch
 // stride over the partial rows, then a fixed shuffle tree (deterministic: same order on every run and rank).
 __global__ void k_glm_finish_tc(uint32_t n, uint32_t chunks, uint32_t ldp, const double* __restrict__ partial,
                                 const double* __restrict__ sx, const float* __restrict__ pts, uint32_t pitch,
-                                uint32_t dim, double* __restrict__ sp) {
+                                uint32_t dim, uint32_t link, double* __restrict__ sp) {
     const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (k >= n) return;
     double s = 0.0;
     for (uint32_t c = lane; c < chunks; c += 32) s += partial[(size_t)c * ldp + k];
-    for (uint32_t i = lane; i < dim; i += 32)
-        s += 0.5 * 0.6931471805599453 * sx[i] * (double)__fmul_rn(pts[(size_t)i * pitch + k], LOG2E);
+    if (link == 0)   // the analytic sum_rows eta / 2 of the softplus split; exp has no such term
+        for (uint32_t i = lane; i < dim; i += 32)
+            s += 0.5 * 0.6931471805599453 * sx[i] * (double)__fmul_rn(pts[(size_t)i * pitch + k], LOG2E);
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) sp[k] = s;

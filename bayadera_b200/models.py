@@ -31,6 +31,7 @@ import numpy as np
 FAST_MATH = 0x1
 ROW_ADDITIVE = 0x2
 GLM_LOGISTIC = 0x4
+GLM_POISSON = 0x8
 
 _SIG = ("const uint32_t data_len, const uint32_t params_len, const REAL* params, "
         "const uint32_t dim, const REAL* x")
@@ -308,6 +309,35 @@ def logistic_regression_model(d: int = 64, prior_sd: float = 10.0) -> DeviceMode
                 _fn("logreg_mcmc_logpdf", body))
     return DeviceModel("logreg", (src,), "logreg_mcmc_logpdf", d, 1, _lim(*([(-1.0, 1.0)] * d)),
                        "logreg_mcmc_logpdf", flags=FAST_MATH | ROW_ADDITIVE | GLM_LOGISTIC,
+                       meta={"row_stride": d + 1, "prior_sd": prior_sd})
+
+
+def poisson_regression_model(d: int = 16, prior_sd: float = 10.0) -> DeviceModel:
+    """Bayesian Poisson regression with log link: data rows are [y, x_1..x_d] (y a count), hyperparams =
+    [1/(2*prior_sd^2)];  logpdf = sum_rows (y*eta - exp(eta)) - sum theta^2/(2 sd^2)  (the log y! constant is dropped).
+
+    Same row-additive GLM interface as ``logistic_regression_model`` with the other log-partition function: the
+    engine streams the dataset once for all walkers (tensor cores for d <= 128); the serial body below is the
+    reference-style per-thread loop (and the oracle)."""
+    prior_body = f"""
+        REAL ss = 0.0f;
+        for (uint32_t i = 0; i < {d}; i++) ss += x[i] * x[i];
+        return - params[0] * ss;"""
+    body = f"""
+        const uint32_t stride = {d + 1};
+        const uint32_t rows = data_len / stride;
+        double acc = 0.0;
+        for (uint32_t r = 0; r < rows; r++) {{
+            const REAL* row = &params[(size_t)r * stride];
+            REAL eta = 0.0f;
+            for (uint32_t i = 0; i < {d}; i++) eta += row[1 + i] * x[i];
+            acc += (double)(row[0] * eta - exp(eta));
+        }}
+        return (REAL)(acc + (double)poisreg_prior(data_len, params_len, &params[data_len], dim, x));"""
+    src = _wrap("#define BAY_GLM_PRIOR poisreg_prior\n", _fn("poisreg_prior", prior_body),
+                _fn("poisreg_mcmc_logpdf", body))
+    return DeviceModel("poisreg", (src,), "poisreg_mcmc_logpdf", d, 1, _lim(*([(-0.5, 0.5)] * d)),
+                       "poisreg_mcmc_logpdf", flags=FAST_MATH | ROW_ADDITIVE | GLM_POISSON,
                        meta={"row_stride": d + 1, "prior_sd": prior_sd})
 
 

@@ -51,6 +51,7 @@ typedef struct bay_sampler bay_sampler; /* replaces GTXStretch, G/:282-541 */
 #define BAY_MODEL_FAST_MATH   0x1u  /* compile with -use_fast_math like G/:630-633 (default of the host mirror) */
 #define BAY_MODEL_ROW_ADDITIVE 0x2u /* model also defines BAY_ROWLIK / BAY_PRIOR */
 #define BAY_MODEL_GLM_LOGISTIC 0x4u /* data rows are [y, x_1..x_D]; likelihood is Bernoulli-logit of x·theta */
+#define BAY_MODEL_GLM_POISSON 0x8u  /* data rows are [y, x_1..x_D]; likelihood is Poisson with log link: y*eta - exp(eta) */
 
 const char *bay_last_error(void);
 const char *bay_version(void);
