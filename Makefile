@@ -11,6 +11,7 @@ $(LIB): $(wildcard $(CSRC)/*.cu $(CSRC)/*.cuh $(CSRC)/*.inc) include/bayadera_b2
 
 oracle:
 	$(MAKE) -C oracle
+	$(MAKE) -C oracle ref
 
 clean:
 	rm -f $(LIB) $(CSRC)/ptxas.log

@@ -42,7 +42,7 @@ def workload(name: str):
     if name == "c1":
         return dict(key="c1", desc="1-D Gaussian(0,1), 2^14 walkers (BASELINE configs[0])", model=models.GAUSSIAN,
                     params=f32([0, 1]), limits=f32([-7, 7]), walkers=2 ** 14, moves=256, a=2.0,
-                    cpu_walkers=2 ** 14)
+                    cpu_walkers=2 ** 14, ref_stem="gaussian_d1")
     if name == "c2":
         params = np.concatenate([models.binomial_lik_params(50, 15), models.beta_params(3, 2)])
         return dict(key="c2", desc="beta-binomial coin posterior, 2^18 walkers (BASELINE configs[1])",
@@ -157,7 +157,14 @@ def cpu_rate(wl: dict, budget_s: float, walkers: int):
     params = wl["params"]
     if params is None:                                # c4: bounded row sample, same generator family
         params = logreg_rows_host(wl["cpu_rows"], wl["model"].dimension)
-    s = orc.OracleStretch(wl["model"], 123, walkers, params, wgs=256)
+    from oracle import ref_text
+    if wl.get("ref_stem") and ref_text.available(wl["ref_stem"]):
+        # the reference's OWN kernel text compiled for the host (oracle/_ref, see oracle/ref_shim/cl_shim.h)
+        s = ref_text.ReferenceTextStretch(wl["ref_stem"], wl["model"], 123, walkers, params, wgs=256)
+        wl["cpu_kind"] = "reference"
+    else:
+        s = orc.OracleStretch(wl["model"], 123, walkers, params, wgs=256)
+        wl["cpu_kind"] = "port"
     s.init_position(123, wl["limits"])
     s.a_bare = wl["a"]
     s.move_bare()                                   # warm-up + calibration
@@ -196,8 +203,11 @@ def run_reference(args, wl: dict, rank: int, world: int):
             "higher_is_better": True, "scaling": "strong" if wl.get("glm") else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "walkers": walkers, "dim": wl["model"].dimension,
-                       "engine": "CPU oracle (C restatement of the reference kernels, OpenMP over walkers)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                       "engine": ("the reference's own OpenCL kernel text compiled by gcc for the host (oracle/_ref), "
+                                  "OpenMP over work-items") if wl.get("ref_stem") else
+                                 "CPU oracle (C restatement of the reference kernels, OpenMP over walkers)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": wl.get("cpu_kind", "port"),
+                             "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -407,7 +417,7 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             r, n, dt, threads = cpu_rate(wl, 12.0, wl["cpu_walkers"])
-            cpu = {"value": r, "unit": UNIT, "cores": threads, "kind": "port",
+            cpu = {"value": r, "unit": UNIT, "cores": threads, "kind": wl.get("cpu_kind", "port"),
                    "sample": f"{wl['cpu_walkers']} walkers x {n} moves ({dt:.1f} s) of workload {wl['key']}, CPU oracle (OpenMP)"
                              + (f", on {wl['cpu_rows']} of {wl['rows']} rows, rate scaled linearly by rows" if wl.get("rows") else "")}
         if wl.get("glm"):   # statically compiled kernel: numbers from the nvcc -Xptxas -v log (profiles/)

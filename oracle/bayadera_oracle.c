@@ -21,6 +21,11 @@
  * uncomplicate/neanderthal 0.25.7-SNAPSHOT, see C/internal/device/nvidia_gtx.clj:648-656);
  * its published algorithm is restated here and pinned by the public KATs.
  *
+ * On top of the goldens, tests/test_oracle_reference_text.py runs this file beside the REFERENCE'S OWN KERNEL TEXT
+ * (K/opencl/engines/amd-gcn-mcmc-stretch.cl compiled by gcc behind oracle/ref_shim/cl_shim.h into oracle/_ref/):
+ * stretch_move_bare and logfn agree bit for bit over 57 steps, init_walkers to 2 ulp (FMA choice), and the
+ * literal_partner mode is that text for DIM = 2.
+ *
  * Build: gcc -O2 -std=c11 -ffp-contract=off -fopenmp -fPIC -shared (see oracle/Makefile).
  * -ffp-contract=off is REQUIRED: the three FMA contractions that the
  * reference's nvcc build performs are written out explicitly with fmaf().
