@@ -71,7 +71,14 @@ int bay_engine_synchronize(bay_engine *e);
 
 /* ---- multi-GPU: one process per GPU; no counterpart in the reference ----
  * The 128-byte ncclUniqueId is produced on rank 0 and distributed by the
- * caller (torch.distributed broadcast in the host mirror). */
+ * caller (torch.distributed broadcast in the host mirror).  Call bay_engine_comm_init BEFORE compiling models.
+ * Afterwards
+ *   - GLM models (BAY_MODEL_GLM_*): walkers replicated, each rank passes ITS rows; per-walker sums are all-reduced;
+ *   - every other model: ONE ensemble, rank r updates its slice of each half (results bit-identical to one GPU).
+ *     Accepted walkers are stored by the kernel into every rank's ensemble over NVLink peer memory (CUDA IPC, up to
+ *     8 ranks of one node; BAY_P2P=0 in the environment selects an NCCL all-gather exchange instead).
+ * Calls on such samplers — create, init-position!, burn-in!, run-sampler!, sample!, histogram!, mean, state
+ * hand-off, release — are COLLECTIVE: every rank makes the same calls in the same order. */
 int bay_nccl_unique_id(uint8_t id_out[128]);
 int bay_engine_comm_init(bay_engine *e, const uint8_t id[128], int nranks, int rank);
 
@@ -93,7 +100,9 @@ int bay_model_kernel_info(bay_model *m, const char *kernel, int *regs, int *loca
 /* ---- sampler: create-sampler [this seed walkers params], P/:120-121, G/:548-610 ----
  * params_host = [data (data_len) || hyperparams (params_size)], copied.
  * Fails with BAY_EINVAL_WALKERS unless walkers >= 2*wgs and walkers % (2*wgs) == 0.
- * With a communicator (bay_engine_comm_init) `walkers` is the GLOBAL count. */
+ * With a communicator (bay_engine_comm_init) `walkers` is the GLOBAL count (a multiple of 2*wgs*nranks for
+ * partitioned samplers).  An owned parameter vector of 64..16128 floats is also mirrored into __constant__ memory
+ * and the sampler runs the program variant that reads it from there (BAY_CPARAMS=0 disables). */
 int bay_sampler_create(bay_model *m, int32_t seed, int64_t walkers, const float *params_host,
                        int64_t params_count, bay_sampler **out);
 /* same, with params already in device memory (the reference borrows a cuda-float vector) */
