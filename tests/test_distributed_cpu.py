@@ -101,3 +101,52 @@ def test_row_sharded_protocol_world2(tmp_path):
     world, port = 2, _free_port()
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert sorted(p.name for p in tmp_path.iterdir()) == ["ok0", "ok1"]
+
+
+def _partition_worker(rank, world, port, out_dir):
+    """Mode A (walker partition): rank r updates only walkers [r*H/R, (r+1)*H/R) of the active half, the updated
+    slices (positions + log-densities) are all-gathered, and the chain must equal the single-process chain bit for
+    bit — the host protocol of engine.cu's `my_slice` / `exchange_half`, run over gloo with the oracle as the kernel."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as orc
+        model = models.therapeutic_touch_model()
+        params, lim = models.therapeutic_touch_data(), model.limits_array()
+        walkers, wgs = 2 * 256 * world * 2, 256
+        D, H = model.dimension, walkers // 2
+        hs = H // world
+        single = orc.OracleStretch(model, 21, walkers, params, wgs=wgs).init_position(22, lim)
+        mine = orc.OracleStretch(model, 21, walkers, params, wgs=wgs).init_position(22, lim)
+        for step in range(4):
+            for half in (0, 1):
+                before_x, before_lp = mine.xs.copy(), mine.lp.copy()
+                mine.a_bare, mine.beta = 1.8, 1.0
+                mine.half_bare(half)                              # the oracle computes the whole half ...
+                act = slice(half * H, (half + 1) * H)
+                xs_half = mine.xs.reshape(walkers, D)[act].copy()
+                lp_half = mine.lp[act].copy()
+                mine.xs[:], mine.lp[:] = before_x, before_lp      # ... but this rank only KEEPS its slice
+                own = slice(rank * hs, (rank + 1) * hs)
+                send = torch.from_numpy(np.concatenate([xs_half[own].reshape(-1), lp_half[own]]))
+                got = [torch.zeros_like(send) for _ in range(world)]
+                dist.all_gather(got, send)                        # exchange_half
+                for r, t in enumerate(got):
+                    t = t.numpy()
+                    dst = slice(half * H + r * hs, half * H + (r + 1) * hs)
+                    mine.xs.reshape(walkers, D)[dst] = t[:hs * D].reshape(hs, D)
+                    mine.lp[dst] = t[hs * D:]
+            mine.bare_counter += 1
+            single.a_bare, single.beta = 1.8, 1.0
+            single.move_bare()
+            assert np.array_equal(mine.xs, single.xs), f"step {step}: partitioned chain left the single-process chain"
+            assert np.array_equal(mine.lp, single.lp, equal_nan=True)
+        (Path(out_dir) / f"ok{rank}").write_text("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_walker_partition_protocol_world2(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_partition_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert sorted(p.name for p in tmp_path.iterdir()) == ["ok0", "ok1"]
