@@ -84,6 +84,17 @@ static int fail(int code, const char* fmt, ...) {
         if (r_ != BAY_OK) return r_; \
     } while (0)
 
+// Scratch device allocation that frees itself on every return path (the CK / TRY macros return early).
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
 // ------------------------------------------------------- lazy driver/nvrtc --
 namespace {
 
