@@ -268,6 +268,7 @@ struct bay_model {
     int glm_link = 0;      // 0 Bernoulli-logit (softplus), 1 Poisson-log (exp)
     bool mirror = false;   // AoS mirror of the ensemble for the partner gather (DIM >= 4, non-GLM)
     bool peers = false;    // kernels store accepted walkers into every rank's ensemble block (multi-GPU mode A)
+    bool pull = false;     // ... or (experimental, BAY_PULL=1) nothing is stored remotely and partner rows are pulled
     // Constant-parameter variant (stretch_program.inc, BAY_CPARAMS): the same program compiled with the parameter
     // vector in __constant__ memory; built on demand for samplers whose parameters fit (cparams_try)
     CUmodule cmod = nullptr;
@@ -302,6 +303,7 @@ struct bay_sampler {
     uint64_t peer_flags_off = 0;        // offset (in 4-byte words) of the barrier flags inside the block
     uint32_t peer_epoch = 0;
     bool cp = false;                    // runs the constant-parameter kernel variant
+    bool remote_stale = false;          // pull mode: other ranks' slices of the local copy are out of date
     bool soa_stale = false;             // peers forwarded mirror rows only: rebuild xs from xa before a read-out
     void* peer_mapped[8] = {nullptr};   // what cudaIpcOpenMemHandle returned (to close on release)
     float* loop_betas = nullptr;        // per-step inverse temperatures (anneal!)
@@ -455,12 +457,17 @@ static bool model_wants_mirror(int dim, uint32_t flags) {
 // so that few CTAs arrive at each grid barrier.
 static int loop_block_for(int dim, int block) { return dim <= 2 ? 1024 : (dim <= 8 ? 512 : block); }
 
+static bool engine_wants_pull(const bay_engine* e) {
+    const char* env = getenv("BAY_PULL");
+    return engine_wants_peers(e) && env && env[0] == '1';
+}
+
 // NVRTC step shared by bay_model_compile and bay_model_compile_check.
 // gtx-stretch-factory (G/:747-757): model sources first, engine kernels after;
 // stretch-options (G/:630-633) retargeted to sm_100a.
 static int nvrtc_build(const char* const* srcs, int nsrc, const char* logfn_name, int dim, int wgs, int block,
                        uint32_t flags, bool peers, bool verbose, std::vector<char>* cubin, std::string* log_out,
-                       int cparams = 0) {
+                       int cparams = 0, bool pull = false) {
     if (!srcs || !logfn_name) return fail(BAY_EINVAL, "NULL argument");
     if (dim < 1 || dim > 4096) return fail(BAY_EINVAL, "dimension %d out of range", dim);
     if (wgs < 32 || wgs > 1024 || (wgs & (wgs - 1))) return fail(BAY_EINVAL, "wgs must be a power of two in [32, 1024], got %d", wgs);
@@ -483,6 +490,7 @@ static int nvrtc_build(const char* const* srcs, int nsrc, const char* logfn_name
         opts.push_back("-DBAY_DIMA=" + std::to_string((dim + 3) / 4 * 4));
     }
     if (peers) opts.push_back("-DBAY_PEERS=1");
+    if (peers && pull) opts.push_back("-DBAY_PULL=1");
     if (flags & BAY_MODEL_GLM_POISSON) opts.push_back("-DBAY_GLM_LINK=1");
     if (cparams > 0) opts.push_back("-DBAY_CPARAMS=" + std::to_string(cparams));
     // ensemble traffic policy (stretch_program.inc, BAY_STREAM): large-DIM models keep a per-thread local array and
@@ -555,7 +563,8 @@ extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsr
     std::vector<char> cubin;
     const bool glm_model = (flags & BAY_GLM_ANY) && dim % 4 == 0;
     const bool peers = engine_wants_peers(e) && !glm_model;
-    TRY(nvrtc_build(srcs, nsrc, logfn_name, dim, e->wgs, bare_block_for(dim), flags, peers, false, &cubin, nullptr));
+    const bool pull = peers && engine_wants_pull(e);
+    TRY(nvrtc_build(srcs, nsrc, logfn_name, dim, e->wgs, bare_block_for(dim), flags, peers, false, &cubin, nullptr, 0, pull));
 
     bay_model* m = new bay_model();
     m->e = e;
@@ -565,6 +574,7 @@ extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsr
     m->block = bare_block_for(dim);
     m->mirror = model_wants_mirror(dim, flags);
     m->peers = peers;
+    m->pull = pull;
     m->dima = (dim + 3) / 4 * 4;
     for (int i = 0; i < nsrc; i++) m->srcs.emplace_back(srcs[i]);
     m->logfn_name = logfn_name;
@@ -651,7 +661,7 @@ static void cparams_try(bay_sampler* s, int64_t params_count) {
         for (auto& t : m->srcs) srcs.push_back(t.c_str());
         std::vector<char> cubin;
         if (nvrtc_build(srcs.data(), (int)srcs.size(), m->logfn_name.c_str(), m->dim, m->e->wgs, m->block, m->flags, m->peers,
-                        false, &cubin, nullptr, kCparamsCap) != BAY_OK) return;
+                        false, &cubin, nullptr, kCparamsCap, m->pull) != BAY_OK) return;
         if (g_cu.ModuleLoadData(&m->cmod, cubin.data()) != CUDA_SUCCESS) { m->cmod = nullptr; return; }
         size_t bytes = 0;
         bool ok = g_cu.ModuleGetFunction(&m->c_bare, m->cmod, "bay_stretch_bare") == CUDA_SUCCESS &&
@@ -1027,7 +1037,32 @@ static int peer_settle(bay_sampler* s) {
 
 // Peers forward only mirror rows (stretch_program.inc, bay_forward_peers): before anything reads the SoA matrix
 // outside a rank's own slice (sample!, histogram!, mean, state hand-off) it is rebuilt from the mirror.
+// Pull mode: a rank only maintains its own slices; before a read-out it copies every other rank's slices (SoA rows,
+// log-densities, mirror rows) out of that rank's block.  The half-step barrier has already made them final.
+static int ensemble_gather(bay_sampler* s) {
+    if (!s->remote_stale) return BAY_OK;
+    bay_engine* e = s->m->e;
+    const size_t W = (size_t)s->W, H = (size_t)s->H, D = (size_t)s->D, hs = H / e->nranks;
+    const size_t dima = s->xa ? (size_t)s->m->dima : 0;
+    for (int r = 0; r < e->nranks; r++) {
+        if (r == e->rank) continue;
+        const float* blk = reinterpret_cast<const float*>((uintptr_t)s->peer_tab.base[r]);
+        for (size_t half = 0; half < 2; half++) {
+            const size_t c0 = half * H + (size_t)r * hs;
+            CK(cudaMemcpy2DAsync(s->xs + c0, W * sizeof(float), blk + c0, W * sizeof(float), hs * sizeof(float), D,
+                                 cudaMemcpyDeviceToDevice, e->stream));
+            CK(cudaMemcpyAsync(s->lp + c0, blk + s->peer_tab.lp_off + c0, hs * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+            if (dima)
+                CK(cudaMemcpyAsync(s->xa + c0 * dima, blk + s->peer_tab.xa_off + c0 * dima, hs * dima * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, e->stream));
+        }
+    }
+    s->remote_stale = false;
+    return BAY_OK;
+}
+
 static int soa_fresh(bay_sampler* s) {
+    TRY(ensemble_gather(s));
     if (!s->soa_stale) return BAY_OK;
     TRY(aos_to_soa(s->m->e, s->xa, 0, (uint64_t)s->m->dima, (uint32_t)s->D, (uint64_t)s->W, s->xs, (uint64_t)s->W));
     s->soa_stale = false;
@@ -1050,7 +1085,13 @@ static int half_bare(bay_sampler* s, int half, uint32_t seed, uint32_t tag, floa
     std::vector<void*> args = {&K, &seed, &tag, &s->data_len, &s->params_len, &s->params, &cmp, &act, &pitch, &lp,
                                &cA, &cB, &cC, &beta, &step, &kb, &ke};
     if (m->mirror) { args.push_back(&cmp_a); args.push_back(&act_a); }
-    if (m->peers) { args.push_back(&s->peer_tab); args.push_back(&col0); s->soa_stale = m->mirror; }
+    uint32_t pull_hs = (uint32_t)(s->H / m->e->nranks), ccol0 = half ? 0u : K;
+    if (m->peers) {
+        args.push_back(&s->peer_tab);
+        args.push_back(&col0);
+        if (m->pull) { args.push_back(&pull_hs); args.push_back(&ccol0); s->remote_stale = true; }
+        else s->soa_stale = m->mirror;
+    }
     TRY(bind_params(s));
     TRY(launch(m->e, fn_bare(s), cdiv(ke - kb, m->block), m->block, args.data()));
     return exchange_half(s, half);
@@ -1072,7 +1113,13 @@ static int half_accu(bay_sampler* s, int half, uint32_t seed, uint32_t tag, floa
     std::vector<void*> args = {&K, &seed, &tag, &s->data_len, &s->params_len, &s->params, &cmp, &act, &pitch, &lp,
                                &s->accept, &s->blk_sums, &cA, &cB, &cC, &step, &accumulate, &kb, &ke};
     if (m->mirror) { args.push_back(&cmp_a); args.push_back(&act_a); }
-    if (m->peers) { args.push_back(&s->peer_tab); args.push_back(&col0); s->soa_stale = m->mirror; }
+    uint32_t pull_hs = (uint32_t)(s->H / m->e->nranks), ccol0 = half ? 0u : K;
+    if (m->peers) {
+        args.push_back(&s->peer_tab);
+        args.push_back(&col0);
+        if (m->pull) { args.push_back(&pull_hs); args.push_back(&ccol0); s->remote_stale = true; }
+        else s->soa_stale = m->mirror;
+    }
     TRY(bind_params(s));
     TRY(launch(m->e, fn_accu(s), cdiv(ke - kb, m->e->wgs), m->e->wgs, args.data()));
     return exchange_half(s, half);
@@ -1083,7 +1130,7 @@ static int half_accu(bay_sampler* s, int half, uint32_t seed, uint32_t tag, floa
 static bool loop_usable(const bay_sampler* s, int64_t n) {
     const bay_model* m = s->m;
     if (m->glm || !m->f_loop || n < 2) return false;
-    if (partitioned(s) && !m->peers) return false;   // the NCCL exchange needs a kernel boundary per half-step
+    if (partitioned(s) && (!m->peers || m->pull)) return false;   // NCCL exchange / pull mode: one kernel per half-step
     uint32_t kb, ke;
     my_slice(s, &kb, &ke);
     if ((int64_t)cdiv(ke - kb, m->loop_block) > loop_capacity(s)) return false;

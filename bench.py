@@ -439,6 +439,9 @@ def main():
                                f"one ensemble of {W_global} walkers partitioned over {world} GPUs, " + (
                                    "NCCL all-gather of the updated slice every half-step"
                                    if os.environ.get("BAY_P2P", "1").startswith("0") else
+                                   "each rank keeps its own slices; partner rows PULLED from the owning rank over "
+                                   "NVLink peer memory + flag barrier every half-step (BAY_PULL=1)"
+                                   if os.environ.get("BAY_PULL", "0") == "1" else
                                    "accepted walkers stored into every peer's ensemble by the stretch kernel (NVLink "
                                    "peer memory) + flag barrier every half-step")),
                            "l2": "flushed between timed steps (256 MiB write)",

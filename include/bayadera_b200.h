@@ -76,7 +76,8 @@ int bay_engine_synchronize(bay_engine *e);
  *   - GLM models (BAY_MODEL_GLM_*): walkers replicated, each rank passes ITS rows; per-walker sums are all-reduced;
  *   - every other model: ONE ensemble, rank r updates its slice of each half (results bit-identical to one GPU).
  *     Accepted walkers are stored by the kernel into every rank's ensemble over NVLink peer memory (CUDA IPC, up to
- *     8 ranks of one node; BAY_P2P=0 in the environment selects an NCCL all-gather exchange instead).
+ *     8 ranks of one node; BAY_P2P=0 in the environment selects an NCCL all-gather exchange instead, BAY_PULL=1
+ *     an experimental mode in which nothing is forwarded and partner rows are read from the owning rank).
  * Calls on such samplers — create, init-position!, burn-in!, run-sampler!, sample!, histogram!, mean, state
  * hand-off, release — are COLLECTIVE: every rank makes the same calls in the same order. */
 int bay_nccl_unique_id(uint8_t id_out[128]);
