@@ -39,6 +39,7 @@ static __inline__ float work_group_reduction_sum_2(float* lacc, float v) { (void
 #define native_log(x) logf(x)
 #define native_powr(x, y) powf((x), (y))
 #define native_sqrt(x) sqrtf(x)
+#define lgamma(x) lgammaf(x)   /* OpenCL's lgamma(float) is single precision */
 static __inline__ float pown(float x, int n) {   /* OpenCL pown: x^n, integer n */
     float r = 1.0f;
     for (int i = 0; i < (n < 0 ? -n : n); i++) r *= x;

@@ -20,6 +20,7 @@ _f32 = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 # (library stem) -> what it was built from; keep in step with oracle/Makefile
 BUILT = {"uniform_d1": ("uniform.cl", "uniform_logpdf", 1),
          "gaussian_d1": ("gaussian.cl", "gaussian_mcmc_logpdf", 1),
+         "beta_binomial_d1": ("beta.cl + binomial.cl + the expanded posterior template", "beta_binomial_mcmc_logpdf", 1),
          "gaussian2_d2": ("ref_shim/gaussian2.cl (ours: a 2-D model to exercise DIM > 1)", "gaussian2_logpdf", 2)}
 
 

@@ -106,3 +106,74 @@ def test_literal_partner_switch_is_the_reference_text_for_dim_2():
     c.half_bare(0)
     moved = (a.xs[:a.H * 2] != before[:a.H * 2]).reshape(-1, 2).any(axis=1)
     assert (a.xs[:a.H * 2].reshape(-1, 2)[moved] != c.xs[:a.H * 2].reshape(-1, 2)[moved]).any(axis=1).mean() > 0.3
+
+
+# ---- the model library (row a6) against the reference's distribution files -----------------------------------
+def _ref_logfn(stem, params, points, params_size):
+    lib = ref_text.load(stem)
+    pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1)
+    params = f32(params).reshape(-1)
+    out = np.zeros(pts.size, dtype=np.float32)
+    lib.ref_logfn(max(0, params.size - params_size), params_size, params, pts, out, pts.size)
+    return out
+
+
+def _our_logfn(model, fn_name, params, points):
+    import dataclasses
+    m = dataclasses.replace(model, mcmc_logpdf=fn_name, name=f"{model.name}_{fn_name}_vs_ref")
+    fn, _keep = orc.compile_model(m)
+    pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1)
+    params = f32(params).reshape(-1)
+    out = np.zeros(pts.size, dtype=np.float32)
+    orc.lib().orc_logfn(fn, pts.size, 1, max(0, params.size - model.params_size), model.params_size, params, pts, out)
+    return out
+
+
+_MODEL_CASES = [
+    ("uniform_logpdf", models.UNIFORM, [-1.0, 2.0], (-1.5, 2.5)),
+    ("gaussian_logpdf", models.GAUSSIAN, [1.5, 0.7], (-3, 5)),
+    ("student_t_logpdf", models.STUDENT_T, [4.0, 0.5, 2.0, -1.67], (-9, 9)),
+    ("beta_logpdf", models.BETA, list(models.beta_params(2.5, 4.0)), (0.01, 0.99)),
+    ("exponential_logpdf", models.EXPONENTIAL, [3.0, 1.0986123], (-0.5, 4)),
+    ("erlang_logpdf", models.ERLANG, [2.0, 3.0, 1.3862944], (0.05, 6)),
+    ("gamma_logpdf", models.GAMMA, [1.7, 2.4, -1.49], (0.05, 9)),
+    ("binomial_logpdf", models.BINOMIAL, [20.0, 0.3], (0, 20)),
+]
+
+
+@pytest.mark.parametrize("fn,model,params,span", _MODEL_CASES, ids=[c[0] for c in _MODEL_CASES])
+def test_model_strings_are_the_reference_arithmetic(fn, model, params, span):
+    """Every built-in family: OUR model source (what NVRTC compiles) and the REFERENCE'S distribution file, both
+    compiled by gcc without FMA contraction and with the same libm, give bit-identical log-densities — the re-authored
+    library kept the reference's arithmetic order."""
+    stem = f"model_{fn}"
+    if not ref_text.available(stem):
+        pytest.skip("reference model text not built")
+    xs = np.linspace(span[0], span[1], 257, dtype=np.float32)
+    ours = _our_logfn(model, fn, params, xs)
+    theirs = _ref_logfn(stem, params, xs, model.params_size)
+    assert np.array_equal(ours, theirs, equal_nan=True), np.nanmax(np.abs(ours - theirs))
+
+
+def test_posterior_template_and_chain_equal_reference_text():
+    """beta-binomial posterior (BASELINE config 2): our posterior_model == the reference's beta.cl + binomial.cl under
+    its posterior template — bit-identical log-densities without contraction; with the device-style contraction
+    the reference text differs by <= 2 ulp in logfn and the CHAIN (every accept decision over 40 steps) is identical."""
+    post = models.beta_binomial_posterior()
+    params = f32(np.concatenate([models.binomial_lik_params(50, 15), models.beta_params(3, 2)]))
+    xs = np.linspace(0.001, 0.999, 513, dtype=np.float32)
+    if ref_text.available("model_beta_binomial_mcmc_logpdf"):
+        ours = _our_logfn(post, post.mcmc_logpdf, params, xs)
+        theirs = _ref_logfn("model_beta_binomial_mcmc_logpdf", params, xs, post.params_size)
+        assert np.array_equal(ours, theirs)
+    if not ref_text.available("beta_binomial_d1"):
+        pytest.skip("reference stretch text for the posterior not built")
+    a = ref_text.ReferenceTextStretch("beta_binomial_d1", post, 5, 4096, params)
+    b = orc.OracleStretch(post, 5, 4096, params)
+    b.init_position(6, f32([0, 1]))
+    a.set_positions(b.xs.copy())
+    ulp = np.abs(a.lp.view(np.int32).astype(np.int64) - b.lp.view(np.int32).astype(np.int64))
+    assert ulp.max() <= 2
+    for s in (a, b):
+        s.burn_in(40, 2.0)
+    assert np.array_equal(a.xs, b.xs)
