@@ -47,6 +47,7 @@ SIGNATURES = {
     "bay_last_error": (C.c_char_p, []),
     "bay_version": (C.c_char_p, []),
     "bay_engine_create": (C.c_int, [C.c_int, C.c_uint64, C.c_int, _pp]),
+    "bay_engine_create_current": (C.c_int, [C.c_uint64, C.c_int, _pp]),
     "bay_engine_release": (C.c_int, [_vp]),
     "bay_engine_processing_elements": (C.c_int, [_vp, C.POINTER(_i64)]),
     "bay_engine_stream": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),

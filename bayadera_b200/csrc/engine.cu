@@ -111,6 +111,10 @@ struct DriverApi {
     CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
     CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
     CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    CUresult (*CtxGetCurrent)(CUcontext*) = nullptr;
+    CUresult (*CtxPushCurrent)(CUcontext) = nullptr;
+    CUresult (*CtxPopCurrent)(CUcontext*) = nullptr;
+    CUresult (*CtxGetDevice)(CUdevice*) = nullptr;
     CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
@@ -174,7 +178,9 @@ int load_driver() {
               drv("cuFuncSetAttribute", &g_cu.FuncSetAttribute) &&
               drv("cuOccupancyMaxActiveBlocksPerMultiprocessor",
                   &g_cu.OccupancyMaxActiveBlocksPerMultiprocessor) &&
-              drv("cuGetErrorString", &g_cu.GetErrorString) &&
+              drv("cuGetErrorString", &g_cu.GetErrorString) && drv("cuCtxGetCurrent", &g_cu.CtxGetCurrent) &&
+              drv("cuCtxPushCurrent", &g_cu.CtxPushCurrent) && drv("cuCtxPopCurrent", &g_cu.CtxPopCurrent) &&
+              drv("cuCtxGetDevice", &g_cu.CtxGetDevice) &&
               drv("cuTensorMapEncodeTiled", &g_cu.TensorMapEncodeTiled);
     if (!ok) return fail(BAY_ECUDA, "CUDA driver entry points unavailable (no NVIDIA driver / GPU?)");
     g_cu.ok = true;
@@ -245,12 +251,15 @@ inline unsigned cdiv(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b
 // ----------------------------------------------------------------- handles --
 struct bay_engine {
     int device = 0;
+    CUcontext ctx = nullptr;      // the context every call of this engine runs in (the caller's, or the device's primary)
+    bool borrowed_ctx = false;    // created by bay_engine_create_current: the caller owns the context
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int wgs = 256;
     int sm_count = 0;
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
+    uint32_t tc_configured = 0;   // GLM tensor-core kernel variants whose shared-memory opt-in is set on this device
 };
 
 struct bay_sampler;
@@ -322,6 +331,9 @@ struct bay_sampler {
     double* macc = nullptr;                   // D x 2
     float* vec_d = nullptr;                   // 4 x D scratch
     float* stage = nullptr;                   // D x W AoS staging for state hand-off (lazy)
+    float* sample_stage = nullptr;            // staging of sample! results bound for host memory (lazy, grown on demand)
+    size_t sample_stage_cap = 0;
+    int64_t params_count = 0;                 // floats in `params` (may be fewer than data_len + params_len)
     // GLM path: repacked dataset, proposals and double-precision log-densities
     uint64_t glm_rows = 0;                    // local rows (this rank's shard)
     float* glm_x = nullptr;                   // rows x D row-major
@@ -348,14 +360,60 @@ struct bay_sampler {
 };
 
 // ---------------------------------------------------------------- plumbing --
-static int use_device(const bay_engine* e) {
-    CK(cudaSetDevice(e->device));
-    return BAY_OK;
-}
+// Every entry point runs inside the engine's context, the way the reference wraps each engine call in
+// (in-context ctx ...) (G/:374, 402, ...): the context is pushed unless it is already current and popped on return,
+// so the caller's context stack is left as it was found.  No entry point calls cudaSetDevice (which would swap the
+// caller's context for the primary one); runtime-API calls below operate on whatever context is current.
+struct CtxScope {
+    int rc = BAY_OK;
+    bool pushed = false;
+    explicit CtxScope(const bay_engine* e) {
+        if (!e || !e->ctx || !g_cu.ok) { rc = fail(BAY_EINVAL, "engine has no CUDA context"); return; }
+        CUcontext cur = nullptr;
+        if (g_cu.CtxGetCurrent(&cur) == CUDA_SUCCESS && cur == e->ctx) return;
+        const CUresult r = g_cu.CtxPushCurrent(e->ctx);
+        if (r != CUDA_SUCCESS) rc = cu_fail(r, "cuCtxPushCurrent");
+        else pushed = true;
+    }
+    ~CtxScope() {
+        CUcontext c = nullptr;
+        if (pushed) g_cu.CtxPopCurrent(&c);
+    }
+    CtxScope(const CtxScope&) = delete;
+    CtxScope& operator=(const CtxScope&) = delete;
+};
+#define USE_ENGINE(e)            \
+    CtxScope ctx_scope_(e);      \
+    if (ctx_scope_.rc != BAY_OK) return ctx_scope_.rc
 
 extern "C" const char* bay_last_error(void) { return g_err.c_str(); }
 extern "C" const char* bay_version(void) { return "bayadera_b200 0.1 (sm_100a)"; }
 extern "C" int64_t bay_launch_count(void) { return g_launches.load(); }
+
+static int engine_finish_create(CUcontext ctx, bool borrowed, int device, uint64_t stream, int wgs, bay_engine** out) {
+    bay_engine* e = new bay_engine();
+    e->device = device;
+    e->ctx = ctx;
+    e->borrowed_ctx = borrowed;
+    e->wgs = wgs;
+    CtxScope scope(e);
+    cudaError_t ce = scope.rc == BAY_OK ? cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device)
+                                        : cudaErrorInvalidValue;
+    if (ce == cudaSuccess) {
+        if (stream) {
+            e->stream = reinterpret_cast<cudaStream_t>(stream);
+        } else {
+            ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+            e->own_stream = ce == cudaSuccess;
+        }
+    }
+    if (ce != cudaSuccess) {
+        delete e;
+        return scope.rc != BAY_OK ? scope.rc : fail(BAY_ECUDA, "engine creation failed: %s", cudaGetErrorString(ce));
+    }
+    *out = e;
+    return BAY_OK;
+}
 
 extern "C" int bay_engine_create(int device, uint64_t stream, int wgs, bay_engine** out) {
     if (!out) return fail(BAY_EINVAL, "out is NULL");
@@ -368,28 +426,44 @@ extern "C" int bay_engine_create(int device, uint64_t stream, int wgs, bay_engin
                     ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0");
     }
     if (device < 0 || device >= count) return fail(BAY_EINVAL, "device %d out of range [0,%d)", device, count);
+    // this entry point asks for the device's PRIMARY context (what torch and the runtime API use); it is bound here,
+    // once, and pushed by every later call if the caller has something else current
     CK(cudaSetDevice(device));
     CK(cudaFree(0));
     TRY(load_driver());
-    bay_engine* e = new bay_engine();
-    e->device = device;
-    e->wgs = wgs;
-    CK(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device));
-    if (stream) {
-        e->stream = reinterpret_cast<cudaStream_t>(stream);
-    } else {
-        CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-        e->own_stream = true;
-    }
-    *out = e;
-    return BAY_OK;
+    CUcontext ctx = nullptr;
+    CUresult cr = g_cu.CtxGetCurrent(&ctx);
+    if (cr != CUDA_SUCCESS || !ctx) return fail(BAY_ECUDA, "no primary context on device %d", device);
+    return engine_finish_create(ctx, false, device, stream, wgs, out);
+}
+
+// The reference never touches the primary context: ClojureCUDA creates a driver-API context (with-default,
+// C/cuda.clj:27-31), every engine call runs (in-context ctx ...) and parameters / results are raw CUdeviceptr of THAT
+// context (Neanderthal cuda-float, G/:558, 798).  This constructor adopts the context that is current on the calling
+// thread, whatever kind it is; the engine allocates, loads its modules and launches in it, so borrowed device
+// pointers (bay_sampler_create_dev, bay_sample(out_is_device = 1), bay_dataset_*(data_is_device = 1)) are valid.
+extern "C" int bay_engine_create_current(uint64_t stream, int wgs, bay_engine** out) {
+    if (!out) return fail(BAY_EINVAL, "out is NULL");
+    if (wgs < 32 || wgs > 1024 || (wgs & (wgs - 1))) return fail(BAY_EINVAL, "wgs must be a power of two in [32, 1024], got %d", wgs);
+    if (load_driver() != BAY_OK)
+        return fail(BAY_ECUDA, "no CUDA device available (driver entry points missing); bayadera_b200 has no CPU fallback");
+    CUcontext ctx = nullptr;
+    CUresult cr = g_cu.CtxGetCurrent(&ctx);
+    if (cr != CUDA_SUCCESS) return cu_fail(cr, "cuCtxGetCurrent");
+    if (!ctx) return fail(BAY_ECUDA, "bay_engine_create_current: no CUDA context is current on the calling thread");
+    CUdevice dev = 0;
+    cr = g_cu.CtxGetDevice(&dev);
+    if (cr != CUDA_SUCCESS) return cu_fail(cr, "cuCtxGetDevice");
+    return engine_finish_create(ctx, true, (int)dev, stream, wgs, out);
 }
 
 extern "C" int bay_engine_release(bay_engine* e) {
     if (!e) return BAY_OK;
-    cudaSetDevice(e->device);
-    if (e->comm && g_nccl.ok) g_nccl.CommDestroy(e->comm);
-    if (e->own_stream) cudaStreamDestroy(e->stream);
+    {
+        CtxScope scope(e);
+        if (e->comm && g_nccl.ok) g_nccl.CommDestroy(e->comm);
+        if (e->own_stream) cudaStreamDestroy(e->stream);
+    }
     delete e;
     return BAY_OK;
 }
@@ -408,7 +482,7 @@ extern "C" int bay_engine_stream(bay_engine* e, uint64_t* s) {
 
 extern "C" int bay_engine_synchronize(bay_engine* e) {
     if (!e) return fail(BAY_EINVAL, "NULL engine");
-    TRY(use_device(e));
+    USE_ENGINE(e);
     CK(cudaStreamSynchronize(e->stream));
     return BAY_OK;
 }
@@ -426,7 +500,7 @@ extern "C" int bay_engine_comm_init(bay_engine* e, const uint8_t id[128], int nr
     if (!e || !id) return fail(BAY_EINVAL, "NULL argument");
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(BAY_EINVAL, "bad rank %d / nranks %d", rank, nranks);
     TRY(load_nccl());
-    TRY(use_device(e));
+    USE_ENGINE(e);
     ncclUniqueId uid;
     memcpy(&uid, id, 128);
     CKNCCL(g_nccl.CommInitRank(&e->comm, nranks, uid, rank));
@@ -558,7 +632,7 @@ extern "C" int bay_model_compile_check(const char* const* srcs, int nsrc, const 
 extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsrc, const char* logfn_name,
                                  int dim, int params_size, uint32_t flags, bay_model** out) {
     if (!e || !out) return fail(BAY_EINVAL, "NULL argument");
-    TRY(use_device(e));
+    USE_ENGINE(e);
     TRY(load_driver());
     std::vector<char> cubin;
     const bool glm_model = (flags & BAY_GLM_ANY) && dim % 4 == 0;
@@ -624,7 +698,7 @@ extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsr
 
 extern "C" int bay_model_release(bay_model* m) {
     if (!m) return BAY_OK;
-    cudaSetDevice(m->e->device);
+    CtxScope scope(m->e);
     if (m->mod && g_cu.ok) g_cu.ModuleUnload(m->mod);
     if (m->cmod && g_cu.ok) g_cu.ModuleUnload(m->cmod);
     delete m;
@@ -697,7 +771,7 @@ static int accu_loop_capacity(const bay_sampler* s) {
 static int bind_params(bay_sampler* s) {
     bay_model* m = s->m;
     if (!s->cp || m->cparams_owner == s) return BAY_OK;
-    CK(cudaMemcpyAsync(reinterpret_cast<void*>(m->cparams), s->params, sizeof(float) * ((size_t)s->data_len + s->params_len),
+    CK(cudaMemcpyAsync(reinterpret_cast<void*>(m->cparams), s->params, sizeof(float) * (size_t)s->params_count,
                        cudaMemcpyDeviceToDevice, m->e->stream));
     m->cparams_owner = s;
     return BAY_OK;
@@ -742,8 +816,9 @@ static int peer_block_alloc(bay_sampler* s) {
     cudaIpcMemHandle_t mine;
     CK(cudaIpcGetMemHandle(&mine, s->peer_block));
     const size_t hb = sizeof(cudaIpcMemHandle_t);
-    char* dev = nullptr;
-    CK(cudaMalloc(&dev, hb * e->nranks));
+    DevBuf dev_buf;
+    CK(dev_buf.alloc(hb * e->nranks));
+    char* dev = dev_buf.as<char>();
     std::vector<cudaIpcMemHandle_t> all((size_t)e->nranks);
     cudaError_t ce = cudaMemcpyAsync(dev + hb * e->rank, &mine, hb, cudaMemcpyHostToDevice, e->stream);
     ncclResult_t nr = ncclSuccess;
@@ -751,7 +826,6 @@ static int peer_block_alloc(bay_sampler* s) {
     if (ce == cudaSuccess && nr == ncclSuccess)
         ce = cudaMemcpyAsync(all.data(), dev, hb * e->nranks, cudaMemcpyDeviceToHost, e->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);   // also: every rank's block is zeroed by now
-    cudaFree(dev);
     if (nr != ncclSuccess) return fail(BAY_ENCCL, "handle exchange failed: %s", g_nccl.GetErrorString(nr));
     if (ce != cudaSuccess) return fail(BAY_ECUDA, "handle exchange failed: %s", cudaGetErrorString(ce));
 
@@ -776,13 +850,13 @@ static int peer_block_alloc(bay_sampler* s) {
 
 // tiny all-reduce used as a host-visible rendezvous of all ranks
 static int comm_rendezvous(bay_engine* e) {
-    int* flag = nullptr;
-    CK(cudaMalloc(&flag, sizeof(int)));
+    DevBuf flag_buf;
+    CK(flag_buf.alloc(sizeof(int)));
+    int* flag = flag_buf.as<int>();
     cudaError_t ce = cudaMemsetAsync(flag, 0, sizeof(int), e->stream);
     ncclResult_t nr = ncclSuccess;
     if (ce == cudaSuccess) nr = g_nccl.AllReduce(flag, flag, 1, ncclInt, ncclSum, e->comm, e->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
-    cudaFree(flag);
     if (nr != ncclSuccess) return fail(BAY_ENCCL, "rendezvous failed: %s", g_nccl.GetErrorString(nr));
     if (ce != cudaSuccess) return fail(BAY_ECUDA, "rendezvous failed: %s", cudaGetErrorString(ce));
     return BAY_OK;
@@ -839,10 +913,13 @@ static int sampler_create_common(bay_model* m, int32_t seed, int64_t walkers, in
     if (walkers < 2 * wgs || walkers % (2 * wgs) != 0 || walkers > (int64_t)1 << 31)
         return fail(BAY_EINVAL_WALKERS, "Number of walkers (%lld) must be a multiple of %d.", (long long)walkers, 2 * wgs);
     if (params_count < 0) return fail(BAY_EINVAL, "negative params_count");
+    // element indices of the ensemble are 32-bit in the kernels (walker index, DIM x W / 4 init counters)
+    if ((uint64_t)walkers * (uint64_t)m->dim >= ((uint64_t)1 << 32))
+        return fail(BAY_EINVAL, "ensemble of %lld walkers x %d dimensions has 2^32 or more elements", (long long)walkers, m->dim);
     if (m->e->comm && m->e->nranks > 1 && !m->glm && walkers % ((int64_t)2 * wgs * m->e->nranks) != 0)
         return fail(BAY_EINVAL_WALKERS, "Number of walkers (%lld) must be a multiple of %d.", (long long)walkers,
                     2 * wgs * m->e->nranks);
-    TRY(use_device(m->e));
+    USE_ENGINE(m->e);
     bay_sampler* s = new bay_sampler();
     s->m = m;
     s->W = walkers;
@@ -852,6 +929,7 @@ static int sampler_create_common(bay_model* m, int32_t seed, int64_t walkers, in
     s->params_len = (uint32_t)m->params_size;
     // G/:559-560: data-len = max(0, entries(params) - params-size)
     s->data_len = (uint32_t)(params_count > m->params_size ? params_count - m->params_size : 0);
+    s->params_count = params_count;
     int r = sampler_alloc(s);
     if (r != BAY_OK) { bay_sampler_release(s); return r; }
     bay_init(s, seed);
@@ -899,14 +977,15 @@ extern "C" int bay_sampler_create_dev(bay_model* m, int32_t seed, int64_t walker
 
 extern "C" int bay_sampler_release(bay_sampler* s) {
     if (!s) return BAY_OK;
-    cudaSetDevice(s->m->e->device);
+    CtxScope scope(s->m->e);
     cudaStreamSynchronize(s->m->e->stream);
     if (s->own_params) cudaFree(s->params);
     if (s->m->cparams_owner == s) s->m->cparams_owner = nullptr;
     glm_release(s);
     peer_block_release(s);   // clears xs / lp / xa when they live in the shared block
     void* bufs[] = {s->xs, s->lp, s->accept, s->blk_sums, s->accept_total, s->means, s->hist_counts, s->mm,
-                    s->limits, s->pdf, s->ranks, s->macc, s->vec_d, s->stage, s->xa, s->loop_bar, s->loop_betas, s->accept_all};
+                    s->limits, s->pdf, s->ranks, s->macc, s->vec_d, s->stage, s->xa, s->loop_bar, s->loop_betas, s->accept_all,
+                    s->sample_stage};
     for (void* b : bufs) if (b) cudaFree(b);
     delete s;
     return BAY_OK;
@@ -952,7 +1031,7 @@ static int launch_logfn_all(bay_sampler* s) {
 extern "C" int bay_init_position_uniform(bay_sampler* s, int32_t seed, const float* limits_host) {
     if (!s || !limits_host) return fail(BAY_EINVAL, "NULL argument");
     bay_engine* e = s->m->e;
-    TRY(use_device(e));
+    USE_ENGINE(e);
     CK(cudaMemcpyAsync(s->limits, limits_host, sizeof(float) * 2 * s->D, cudaMemcpyHostToDevice, e->stream));
     const uint32_t n4 = (uint32_t)((uint64_t)s->D * s->W / 4);
     bay::k_init_walkers<<<cdiv(n4, 256), 256, 0, e->stream>>>(n4, (uint32_t)s->D, (uint32_t)seed, s->limits, s->xs,
@@ -972,7 +1051,7 @@ extern "C" int bay_init_position_from(bay_sampler* s, const bay_sampler* other) 
     if (!s || !other) return fail(BAY_EINVAL, "NULL argument");
     if (s->W != other->W || s->D != other->D) return fail(BAY_EINVAL, "samplers differ in shape");
     bay_engine* e = s->m->e;
-    TRY(use_device(e));
+    USE_ENGINE(e);
     TRY(soa_fresh(const_cast<bay_sampler*>(other)));
     CK(cudaMemcpyAsync(s->xs, other->xs, sizeof(float) * (size_t)s->D * s->W, cudaMemcpyDeviceToDevice, e->stream));
     TRY(peer_settle(const_cast<bay_sampler*>(other)));
@@ -1199,7 +1278,7 @@ static int move_bare_n(bay_sampler* s, int64_t n, const float* betas /* nullable
 
 extern "C" int bay_move_bare(bay_sampler* s) {
     if (!s) return fail(BAY_EINVAL, "NULL sampler");
-    TRY(use_device(s->m->e));
+    USE_ENGINE(s->m->e);
     return move_bare_n(s, 1, nullptr);
 }
 
@@ -1208,7 +1287,7 @@ extern "C" int bay_move_bare(bay_sampler* s) {
 // (T/internal/nvidia_gtx_test.clj:217-235).  half 0 = odd launch, 1 = even launch.
 extern "C" int bay_move_bare_half(bay_sampler* s, int half) {
     if (!s || (half != 0 && half != 1)) return fail(BAY_EINVAL, "bad argument");
-    TRY(use_device(s->m->e));
+    USE_ENGINE(s->m->e);
     float cA, cB, cC;
     stretch_coeffs(s->a_bare, &cA, &cB, &cC);
     return half_bare(s, half, (uint32_t)(s->bare_seed + half), half ? 4444u : 3333u, cA, cB, cC, s->beta,
@@ -1230,7 +1309,7 @@ extern "C" int bay_set_temperature(bay_sampler* s, float t) {
 // burn-in! G/:419-429
 extern "C" int bay_burn_in(bay_sampler* s, int64_t n, float a) {
     if (!s || n < 0) return fail(BAY_EINVAL, "bad argument");
-    TRY(use_device(s->m->e));
+    USE_ENGINE(s->m->e);
     s->a_bare = a;
     s->beta = 1.0f;
     TRY(move_bare_n(s, n, nullptr));
@@ -1241,7 +1320,7 @@ extern "C" int bay_burn_in(bay_sampler* s, int64_t n, float a) {
 // anneal! G/:430-440
 extern "C" int bay_anneal(bay_sampler* s, const float* temperature_host, int64_t n, float a) {
     if (!s || n < 0 || (n > 0 && !temperature_host)) return fail(BAY_EINVAL, "bad argument");
-    TRY(use_device(s->m->e));
+    USE_ENGINE(s->m->e);
     s->a_bare = a;
     std::vector<float> betas((size_t)n);
     for (int64_t i = 0; i < n; i++) betas[i] = (float)(1.0 / (double)temperature_host[i]);
@@ -1272,7 +1351,7 @@ static int ensure_means(bay_sampler* s, int64_t n) {
 extern "C" int bay_init_move(bay_sampler* s, float a) {
     if (!s) return fail(BAY_EINVAL, "NULL sampler");
     bay_engine* e = s->m->e;
-    TRY(use_device(e));
+    USE_ENGINE(e);
     s->move_seed += 2;
     s->move_counter = 0;
     s->a_move = a;
@@ -1286,7 +1365,7 @@ extern "C" int bay_init_move(bay_sampler* s, float a) {
 extern "C" int bay_move(bay_sampler* s) {
     if (!s) return fail(BAY_EINVAL, "NULL sampler");
     bay_engine* e = s->m->e;
-    TRY(use_device(e));
+    USE_ENGINE(e);
     float cA, cB, cC;
     stretch_coeffs(s->a_move, &cA, &cB, &cC);
     TRY(ensure_means(s, s->means_n + 1));

@@ -238,30 +238,58 @@ __global__ void k_uint_to_real(uint32_t bins, uint32_t dim, float alpha,
     }
 }
 
-// bitonic_local (estimate.cu:117-147): the same compare-exchange network, one
-// block of `bins` threads per dimension, so that the order inside groups of
-// equal mass matches the reference's too.
-__global__ void k_bin_ranks(uint32_t bins, const float* __restrict__ pdf, float* __restrict__ ranks) {
-    extern __shared__ float2 aux[];
-    const uint32_t lid = threadIdx.x;
-    const uint32_t gid = blockIdx.x * bins + lid;
-    float2 value = make_float2((float)lid, pdf[gid]);
-    aux[lid] = value;
-    __syncthreads();
-    for (uint32_t length = 1; length < bins; length <<= 1) {
-        const bool direction = ((lid & (length << 1)) != 0);
-        for (uint32_t inc = length; inc > 0; inc >>= 1) {
-            const uint32_t j = lid ^ inc;
-            const float2 other = aux[j];
-            const bool smaller = (value.y < other.y) || (other.y == value.y && j < lid);
-            const bool swap = smaller ^ (j < lid) ^ direction;
-            value = swap ? other : value;
-            __syncthreads();
-            aux[lid] = value;
-            __syncthreads();
+// Bin ranking (replaces bitonic_local, estimate.cu:117-147): bins of one dimension ordered by decreasing mass, the
+// input of hdi-rank-count (C/util.clj:52-65).  ONE WARP per dimension keeps the whole column in registers: entry
+// e = lane + 32*slot (slot < bins/32) lives in register `slot` of `lane`, so a comparator of span < 32 is a lane
+// shuffle and one of span >= 32 a register-to-register exchange inside the lane — no shared memory, no block
+// barrier (the reference stages the column in shared memory behind two __syncthreads per comparator level).
+// The comparator schedule is the classic bitonic one (runs of length 2, 4, .., bins; spans run/2 .. 1), which is
+// what fixes the order INSIDE groups of equal mass: lower entry p and upper entry q = p + span exchange iff
+//     (mass[p] < mass[q]) != ascending(p, run),   ascending(p, run) = bit `run` of p,
+// i.e. descending runs leave ties in place and ascending runs exchange them.  The oracle simulates the reference's
+// network, so equal-mass groups (empty bins, mostly) come out in the reference's order.
+template <int SLOTS>
+__global__ void __launch_bounds__(32) k_bin_ranks(const float* __restrict__ pdf, float* __restrict__ ranks) {
+    constexpr uint32_t bins = 32u * SLOTS;       // compile-time, so that every register index below is static
+    const uint32_t lane = threadIdx.x;
+    const float* col = pdf + (size_t)blockIdx.x * bins;
+    float mass[SLOTS];
+    uint32_t bin[SLOTS];
+#pragma unroll
+    for (int s = 0; s < SLOTS; s++) { bin[s] = lane + 32u * s; mass[s] = col[bin[s]]; }
+#pragma unroll
+    for (uint32_t run = 2; run <= bins; run <<= 1) {
+#pragma unroll
+        for (uint32_t span = run >> 1; span >= 1; span >>= 1) {
+            if (span >= 32u) {
+                const int ds = (int)(span >> 5);             // partner sits ds registers away in the same lane
+#pragma unroll
+                for (int s = 0; s < SLOTS; s++) {
+                    if ((s & ds) || s + ds >= SLOTS) continue;   // visit each pair once, from its lower entry
+                    const uint32_t p = lane + 32u * s;
+                    const bool asc = (p & run) != 0u;
+                    if ((mass[s] < mass[s + ds]) != asc) {
+                        const float tm = mass[s]; mass[s] = mass[s + ds]; mass[s + ds] = tm;
+                        const uint32_t tb = bin[s]; bin[s] = bin[s + ds]; bin[s + ds] = tb;
+                    }
+                }
+            } else {
+                const bool upper = (lane & span) != 0u;
+#pragma unroll
+                for (int s = 0; s < SLOTS; s++) {
+                    const float om = __shfl_xor_sync(0xffffffffu, mass[s], span);
+                    const uint32_t ob = __shfl_xor_sync(0xffffffffu, bin[s], span);
+                    const uint32_t p = (lane & ~span) + 32u * s;           // the pair's lower entry
+                    const bool asc = (p & run) != 0u;
+                    const float lo_m = upper ? om : mass[s], hi_m = upper ? mass[s] : om;
+                    if ((lo_m < hi_m) != asc) { mass[s] = om; bin[s] = ob; }
+                }
+            }
         }
     }
-    ranks[gid] = value.x;
+    float* out = ranks + (size_t)blockIdx.x * bins;
+#pragma unroll
+    for (int s = 0; s < SLOTS; s++) out[lane + 32u * s] = (float)bin[s];
 }
 
 // --------------------------------------------------------- mean / variance --

@@ -71,10 +71,14 @@ class B200BayaderaFactory:
     ``stream`` is a raw CUDA stream handle (e.g. ``torch.cuda.current_stream().cuda_stream``);
     0 lets the engine create its own.  The reference's default WGS is max-block-dim-x = 1024."""
 
-    def __init__(self, device: int = 0, stream: int = 0, wgs: int = 1024):
+    def __init__(self, device: int = 0, stream: int = 0, wgs: int = 1024, current_context: bool = False):
         self._L = _lib.load()
         h = C.c_void_p()
-        check(self._L.bay_engine_create(device, stream, wgs, C.byref(h)))
+        if current_context:
+            # adopt the CUDA context current on this thread (ClojureCUDA's with-default context, cuda.clj:27-31)
+            check(self._L.bay_engine_create_current(stream, wgs, C.byref(h)))
+        else:
+            check(self._L.bay_engine_create(device, stream, wgs, C.byref(h)))
         self._h, self.device, self.wgs = h, device, wgs
         self._dataset_engine = B200DatasetEngine(self)
         self._acor_engine = B200AcorEngine(self)

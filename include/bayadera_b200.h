@@ -63,6 +63,16 @@ const char *bay_version(void);
  * (power of two, 32..1024; the reference default is max-block-dim-x = 1024,
  * its tests use 256). */
 int bay_engine_create(int device, uint64_t stream, int wgs, bay_engine **out);
+/* The same engine inside the CUDA context that is CURRENT on the calling thread — the reference's situation:
+ * ClojureCUDA's with-default creates a driver-API context (C/cuda.clj:27-31, C = the reference's
+ * src/clojure/uncomplicate/bayadera/), gtx-bayadera-factory receives it (G/:791-807), every engine call runs inside
+ * (in-context ctx ...) (G/:374, 402, ...) and parameter / result buffers are raw CUdeviceptr of that context
+ * (Neanderthal cuda-float, G/:558, 798).  Nothing is bound to the primary context: the engine allocates, loads its
+ * NVRTC modules and launches in the adopted context, so device pointers of that context can be passed to
+ * bay_sampler_create_dev, bay_sample(out_is_device = 1) and bay_dataset_*(data_is_device = 1).  The caller keeps
+ * ownership of the context and must release the engine's handles before destroying it.
+ * Either way every entry point pushes the engine's context if it is not already current and pops it on return. */
+int bay_engine_create_current(uint64_t stream, int wgs, bay_engine **out);
 int bay_engine_release(bay_engine *e);
 /* processing-elements, P/:138, G/:788-789  (= SM count * WGS) */
 int bay_engine_processing_elements(bay_engine *e, int64_t *out);
