@@ -100,6 +100,7 @@ SIGNATURES = {
     "bay_hdi_histogram": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp, _vp, C.c_int]),
     "bay_mix": (C.c_int, [_vp, _i64, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                           C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "bay_glm_loglik_probe": (C.c_int, [_vp, _f32, _i64, C.c_int, _vp]),
     "bay_launch_count": (_i64, []),
 }
 

@@ -273,6 +273,7 @@ struct bay_model {
     int loop_block = 128;    // its CTA size
     // GLM (row-additive Bernoulli-logit) path, present iff `glm`
     CUfunction f_glm_propose = nullptr, f_glm_loglik = nullptr, f_glm_lp_init = nullptr, f_glm_accept = nullptr;
+    CUfunction f_glm_loglik64 = nullptr;   // fp64 yardstick of the likelihood (bay_glm_loglik_probe)
     bool glm = false;
     int glm_link = 0;      // 0 Bernoulli-logit (softplus), 1 Poisson-log (exp)
     bool mirror = false;   // AoS mirror of the ensemble for the partner gather (DIM >= 4, non-GLM)
@@ -680,7 +681,8 @@ extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsr
     if ((flags & BAY_GLM_ANY) && dim % 4 == 0) {
         struct { const char* name; CUfunction* f; } gfns[] = {
             {"bay_glm_propose", &m->f_glm_propose}, {"bay_glm_loglik", &m->f_glm_loglik},
-            {"bay_glm_lp_init", &m->f_glm_lp_init}, {"bay_glm_accept", &m->f_glm_accept}};
+            {"bay_glm_lp_init", &m->f_glm_lp_init}, {"bay_glm_accept", &m->f_glm_accept},
+            {"bay_glm_loglik_f64", &m->f_glm_loglik64}};
         for (auto& fn : gfns) {
             cr = g_cu.ModuleGetFunction(fn.f, m->mod, fn.name);
             if (cr != CUDA_SUCCESS) {
@@ -794,6 +796,9 @@ static void stretch_coeffs(float a, float* cA, float* cB, float* cC) {
     *cB = 2.0f * o;
     *cC = inv;
 }
+
+static int aos_to_soa(bay_engine* e, const float* in, uint64_t offset, uint64_t ld, uint32_t dim, uint64_t n, float* out,
+                      uint64_t pitch);
 
 #include "engine_glm.inc"
 

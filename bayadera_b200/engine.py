@@ -365,6 +365,14 @@ class B200Stretch:
         check(self._L.bay_set_state64(self._h, ptr(x), ptr(l)))
         return self
 
+    def glm_loglik_probe(self, points, method: int = 0) -> np.ndarray:
+        """Row-additive GLM samplers: sum over the dataset of A(x_row . point) for each of the given points
+        ((n, DIM) array), by method 0 = the sampler's own path (tensor cores when eligible), 1 = fp32 SIMT, 2 = fp64."""
+        pts = _f32(points).reshape(-1, self.DIM)
+        out = np.zeros(pts.shape[0], dtype=np.float64)
+        check(self._L.bay_glm_loglik_probe(self._h, pts.reshape(-1), pts.shape[0], method, ptr(out)))
+        return out
+
     def release(self) -> None:
         if self._h:
             self._L.bay_sampler_release(self._h)

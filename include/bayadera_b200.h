@@ -229,6 +229,14 @@ int bay_hdi_histogram(bay_engine *e, int bins, int dim, const float *limits_host
 int bay_mix(bay_sampler *s, int64_t step, double dimension_power, int schedule, double schedule_power, double a,
             double min_acc, double max_acc, double *out_a, double *out_acc_rate, double *out_acc_rate_2);
 
+/* ---- row-additive GLM path: precision probe (no counterpart in the reference, whose LOGFN loops over the dataset
+ * serially in every thread, K/distributions/gaussian.cu:40-42) ----
+ * sums_host[k] = sum over ALL ranks' rows of A(x_row . point_k) (A = softplus or exp) for n <= walkers caller points
+ * (DIM x n, column = point).  method 0: the path the sampler itself runs (tcgen05 tensor cores when eligible),
+ * 1: the fp32 SIMT kernel, 2: the same traversal in fp64 — the yardstick for the error of the Δlogp the accept test
+ * consumes at full dataset size.  Collective on row-sharded samplers. */
+int bay_glm_loglik_probe(bay_sampler *s, const float *points_host, int64_t n, int method, double *sums_host);
+
 /* profiling counters: kernels launched by this library on the calling process */
 int64_t bay_launch_count(void);
 

@@ -71,6 +71,24 @@ def test_nvrtc_builds_model_for_sm100a(model):
         assert kernel in log
 
 
+@pytest.mark.parametrize("wgs", [32, 512, 1024])
+@pytest.mark.parametrize("model", [models.GAUSSIAN, models.therapeutic_touch_model(), models.logistic_regression_model(64)],
+                         ids=lambda m: m.name)
+def test_nvrtc_builds_at_every_work_group_size(model, wgs):
+    """The reference's default WGS is max-block-dim-x = 1024 (nvidia_gtx.clj:803-807): the accu kernels' staging tile
+    must fit static shared memory there (it is capped at 8 dimensions per round)."""
+    rc, nbytes, log = _compile_check(model, wgs=wgs)
+    assert rc == 0, log
+    assert "bay_stretch_accu" in log
+
+
+def test_nvrtc_builds_wide_glm_model():
+    """DIM = 192 > the tensor-core path's 128: the SIMT likelihood's row tile shrinks so that it still fits."""
+    rc, _, log = _compile_check(models.logistic_regression_model(192))
+    assert rc == 0, log
+    assert "bay_glm_loglik" in log
+
+
 def test_nvrtc_error_is_reported():
     bad = models.DeviceModel("bad", ("extern \"C\" { inline REAL bad_logpdf(int x) { return undefined_symbol; } }",),
                              "bad_logpdf")

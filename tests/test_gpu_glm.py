@@ -212,3 +212,67 @@ def test_poisson_posterior_recovers_truth(factory):
     s.burn_in(600, 2.0)
     x = s.sample().astype(np.float64)
     assert np.abs(x.mean(axis=0) - theta).max() < 0.08, np.abs(x.mean(axis=0) - theta).max()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Parity at the size that is benchmarked: D = 64, 10^7 rows (BASELINE config 4).  Log-densities are ~ -5e6 there
+# and the accept test consumes O(1) differences, so relative tolerances on the log-density say nothing; what is
+# held against an fp64 evaluation of the SAME points is the Δlogp of (current, proposed) pairs and the accept mask.
+# ---------------------------------------------------------------------------------------------------------------
+def _device_rows(rows, d, seed):
+    """bench.py's generator (X ~ N(0,1), theta* ~ N(0, 1/8), y ~ Bernoulli(sigmoid(X theta*))) on the device."""
+    import torch
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    out = torch.empty(rows * (d + 1) + 1, dtype=torch.float32, device=dev)
+    mat = out[:-1].view(rows, d + 1)
+    mat[:, 1:].normal_(generator=g)
+    theta = torch.randn(d, generator=g, device=dev) / (8.0 ** 0.5)
+    p = torch.sigmoid(mat[:, 1:] @ theta)
+    mat[:, 0] = (torch.rand(rows, generator=g, device=dev) < p).float()
+    out[-1] = 1.0 / 200.0
+    torch.cuda.synchronize()
+    return out, theta.cpu().numpy().astype(np.float64)
+
+
+def test_glm_delta_logp_and_accept_mask_at_bench_size(factory):
+    d, rows, pairs = 64, 10 ** 7, 1024
+    model = models.logistic_regression_model(d)
+    data, theta = _device_rows(rows, d, 2024)
+    sampler = factory.mcmc_factory(model).create_sampler(123, 2 * pairs, bb.DeviceParams.from_torch(data))
+    # walkers at the posterior's own scale around the generating coefficients (sd ~ 1/sqrt(rows * 0.2) = 7e-4), the
+    # regime the timed chain lives in; proposals are stretch moves between random pairs of them
+    rng = np.random.default_rng(99)
+    cur = (theta[None, :] + 7e-4 * rng.standard_normal((pairs, d))).astype(np.float32)
+    other = (theta[None, :] + 7e-4 * rng.standard_normal((pairs, d))).astype(np.float32)
+    a = 1.2
+    u = rng.random(pairs)
+    z = (((a - 1.0) * u + 1.0) ** 2 / a).astype(np.float32)              # g(z) ~ 1/sqrt(z) on [1/a, a]
+    prop = (other + z[:, None] * (cur - other)).astype(np.float32)
+    pts = np.concatenate([cur, prop])
+    sums = {m: sampler.glm_loglik_probe(pts, m) for m in (0, 1, 2)}
+    ref = sums[2][pairs:] - sums[2][:pairs]                                # fp64 Δ(sum softplus), proposed - current
+    assert np.all(np.isfinite(ref)) and 0.05 < np.abs(ref).mean() < 1e4   # O(1)..O(100) differences of ~7e6 sums
+    err_tc = np.abs((sums[0][pairs:] - sums[0][:pairs]) - ref)
+    err_simt = np.abs((sums[1][pairs:] - sums[1][:pairs]) - ref)
+    print(f"|dlogp_tc - dlogp_f64|: max {err_tc.max():.3e} mean {err_tc.mean():.3e};  "
+          f"fp32 SIMT: max {err_simt.max():.3e} mean {err_simt.mean():.3e};  |dlogp| mean {np.abs(ref).mean():.3f}")
+    assert err_tc.max() < 1e-2, err_tc.max()
+    # the accept test z^(D-1) exp(Δlogp) >= u with Δlogp = sy.(θp - θc) - Δ(sum softplus) + Δprior: the first and last
+    # terms are computed identically on both paths, so they are taken from fp64 host arithmetic here
+    xf = data[:-1].view(rows, d + 1)
+    sy = (xf[:, 1:].double() * xf[:, :1].double()).sum(dim=0).cpu().numpy()
+    lin = (prop.astype(np.float64) - cur.astype(np.float64)) @ sy
+    dprior = -(1.0 / 200.0) * ((prop.astype(np.float64) ** 2).sum(1) - (cur.astype(np.float64) ** 2).sum(1))
+    uz = rng.random(pairs)
+
+    def mask(dsp):
+        return uz <= z.astype(np.float64) ** (d - 1) * np.exp(np.minimum(lin - dsp + dprior, 50.0))
+
+    m64, mtc = mask(ref), mask(sums[0][pairs:] - sums[0][:pairs])
+    assert 0.02 < m64.mean() < 0.98
+    assert (m64 != mtc).sum() <= 2, int((m64 != mtc).sum())              # only exact near-ties may flip
+    # absolute level: the summed log-partition itself, against fp64, well inside the north-star's 1e-5 relative
+    assert np.abs(sums[0] - sums[2]).max() < 1e-7 * np.abs(sums[2]).max()
+    sampler.release()
