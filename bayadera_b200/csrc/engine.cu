@@ -18,6 +18,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <nvrtc.h>
+#include <nvtx3/nvToolsExt.h>   // header-only; a no-op unless a profiler injects itself
 
 #include <atomic>
 #include <cmath>
@@ -383,8 +384,15 @@ struct CtxScope {
     CtxScope(const CtxScope&) = delete;
     CtxScope& operator=(const CtxScope&) = delete;
 };
-#define USE_ENGINE(e)            \
-    CtxScope ctx_scope_(e);      \
+// NVTX range named after the C-ABI entry point (the reference has no tracing at all): shows up as
+// bay_burn_in / bay_histogram / ... on the nsys / ncu timeline.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#define USE_ENGINE(e)                  \
+    NvtxRange nvtx_range_(__func__);   \
+    CtxScope ctx_scope_(e);            \
     if (ctx_scope_.rc != BAY_OK) return ctx_scope_.rc
 
 extern "C" const char* bay_last_error(void) { return g_err.c_str(); }

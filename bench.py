@@ -151,9 +151,22 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------ reference --
+def job_config(wl: dict, args) -> dict:
+    """The workload both arms are measured on (identical in the b200 and the reference line)."""
+    cfg = {"workload": wl["desc"], "walkers": wl["walkers"], "dim": wl["model"].dimension,
+           "moves_per_step": wl["moves"], "a": wl["a"], "wgs": args.wgs}
+    if wl.get("rows"):
+        cfg["rows"] = wl["rows"]
+    return cfg
+
+
 def cpu_rate(wl: dict, budget_s: float, walkers: int):
-    """walker-steps/s of the CPU oracle (all host threads) on a bounded sample of the workload."""
+    """walker-steps/s of the CPU oracle (all host threads) on a bounded sample of the workload.  The cost of a
+    walker-step does not depend on the ensemble size (every walker evaluates the model once per step), so the rate
+    measured on `walkers` walkers is the rate of the config's ensemble."""
     from oracle import oracle as orc
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: ask for all host cores explicitly
+    orc.lib().orc_set_num_threads(os.cpu_count() or 1)
     params = wl["params"]
     if params is None:                                # c4: bounded row sample, same generator family
         params = logreg_rows_host(wl["cpu_rows"], wl["model"].dimension)
@@ -195,19 +208,20 @@ def run_reference(args, wl: dict, rank: int, world: int):
         rates.append(r)
         total_t += dt
     value = float(np.mean(rates))
-    sample = f"{walkers} walkers x ~{n} moves per step ({budget:.0f} s budget) of workload {wl['key']}"
+    sample = (f"{walkers} of the config's {wl['walkers']} walkers (cost per walker-step is independent of the ensemble "
+              f"size) x ~{n} moves per step ({budget:.0f} s budget) of workload {wl['key']}")
     if wl.get("rows"):
-        sample += f", on {wl['cpu_rows']} of {wl['rows']} rows, rate scaled linearly by rows"
+        sample += f", on {wl['cpu_rows']} of {wl['rows']} rows, rate scaled linearly by rows (cost is linear in rows)"
+    kind = wl.get("cpu_kind", "port")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps,
             "higher_is_better": True, "scaling": "strong" if wl.get("glm") else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "walkers": walkers, "dim": wl["model"].dimension,
-                       "engine": ("the reference's own OpenCL kernel text compiled by gcc for the host (oracle/_ref), "
-                                  "OpenMP over work-items") if wl.get("ref_stem") else
-                                 "CPU oracle (C restatement of the reference kernels, OpenMP over walkers)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": wl.get("cpu_kind", "port"),
-                             "sample": sample},
+            "config": job_config(wl, args),
+            "engine": ("the reference's own OpenCL kernel text compiled by gcc for the host (oracle/_ref), "
+                       "OpenMP over work-items") if kind == "reference" else
+                      "CPU oracle (C restatement of the reference kernels, OpenMP over walkers)",
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -262,6 +276,8 @@ def main():
     ap.add_argument("--walkers", type=int, default=0)
     ap.add_argument("--wgs", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--no-mode-a", action="store_true", help="skip the c5 walker-partition companion measurement")
     ap.add_argument("--strong", action="store_true",
                     help="walker-partitioned workloads: keep the config's TOTAL ensemble and split it over the GPUs "
                          "(default: the config's ensemble per GPU, weak scaling)")
@@ -329,7 +345,13 @@ def main():
     if partition and args.strong:
         W = max(W // world // (2 * args.wgs), 1) * 2 * args.wgs     # this GPU's share of the config's ensemble
     W_global = W * world if partition else W
+    # one-off cost of create-sampler (G/:548-610): for the GLM path it includes splitting the dataset into the bf16
+    # hi/lo planes the tensor cores read and the X^T y / column-sum passes — reported, not part of a step
+    barrier()
+    t0 = time.perf_counter()
     sampler = sfactory.create_sampler(123, W_global, params)
+    factory.synchronize()
+    setup_s = time.perf_counter() - t0
     sampler.init_position(1000, wl["limits"])
     sampler.burn_in(max(64, M), a)                      # leave the initial box before timing
     p_acc = sampler.acc_rate(a)
@@ -373,6 +395,34 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
 
+    # ---- parity self-checks, outside every timed region (bayadera_b200/selfcheck.py) --------------------------------
+    parity = {}
+    if not args.no_parity_check:
+        from bayadera_b200 import selfcheck
+        if wl.get("glm"):
+            # the timed sampler itself, at the full dataset: Δlogp of stretch proposals around the current ensemble
+            # mean, tensor-core path against the fp64 traversal of the same rows (all-reduced over the row shards)
+            centre = xs0.astype(np.float64).mean(axis=0)
+            spread = float(xs0.astype(np.float64).std(axis=0).mean())
+            parity["glm_dlogp_vs_fp64"] = selfcheck.glm_delta_logp(sampler, centre, max(spread, 1e-6), pairs=128, a=a)
+        if world > 1:
+            single = bb.B200BayaderaFactory(device=local_rank, stream=stream.cuda_stream, wgs=args.wgs)
+            parity["mode_a_partition_vs_1gpu"] = selfcheck.mode_a_bit_identity(factory, single, world)
+            parity["mode_b_row_shards_vs_1gpu"] = selfcheck.mode_b_replicas(factory, single, rank, world)
+        parity["ok"] = all(v.get("ok", False) for v in parity.values())
+        ok_t = torch.tensor([1 if parity["ok"] else 0], dtype=torch.int32, device="cuda")
+        if world > 1:
+            dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+        parity["ok"] = bool(int(ok_t[0]))
+        parity["verdict"] = "ok" if parity["ok"] else "MISMATCH"
+
+    # ---- mode A companion measurement (BASELINE configs[4]): the 100-D Gaussian with the config's TOTAL ensemble of
+    # 2^20 walkers partitioned over the GPUs (strong scaling), so that the driver's 1/2/4/8-GPU runs of this file also
+    # carry the walker-partition path.  Same timing rules as the main line.
+    mode_a = None
+    if wl["key"] == "c4" and not args.no_mode_a:
+        mode_a = run_mode_a(args, torch, dist, bb, factory, stream, flush, barrier, rank, world)
+
     total_ws = (1.0 if sharded else float(world)) * W * M * args.steps
     value = total_ws / (dev_ms * 1e-3)
     e2e_value = total_ws / (e2e_ms * 1e-3)
@@ -398,13 +448,13 @@ def main():
                 "launch_us": per_launch_ms * 1e3,
                 "executed_mma_tflops": 3.0 * achieved,
                 "note": "achieved counts ALGORITHMIC flops (2*rows*D per walker); fp32-level accuracy from bf16 inputs "
-                        "takes a 3-term split, so the tensor pipe executes 3x that and frac cannot exceed 1/3; the "
-                        "kernel's binding unit is MUFU (one ex2 per row x walker), see DESIGN.md 4.2",
+                        "takes a 3-term split, so the tensor pipe executes 3x that and frac cannot exceed 1/3; "
+                        "see DESIGN.md 4.2 for the pipe utilisations ncu reports",
                 "hbm_view": {"bytes_per_launch": flops_per_launch / min(W // 2, 512) * 2.0,
                              "achieved_GBps": flops_per_launch / min(W // 2, 512) * 2.0 / (per_launch_ms * 1e-3) / 1e9,
                              "note": "dataset bytes (bf16 hi+lo planes = 4 B/element) streamed once per launch"}}
     else:
-        kernel_name = "bay_stretch_bare"
+        kernel_name = sampler_kernel_name(sampler)
         bytes_per_launch = (W / 2) * algorithmic_bytes_per_walker_step(D, p_acc)
         peak = float(peaks["hbm_gbs"]) if peaks else 6650.0
         achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
@@ -412,50 +462,96 @@ def main():
                 **ncu_traffic(wl["key"], kernel_name), "kernel": kernel_name, "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch,
                 "launch_us": per_launch_ms * 1e3}
+        if W * D * 4 < 64 << 20:
+            # the state of configs 1-3 is L2-resident; what bounds them is the latency of a half-step
+            # (launch or grid barrier + a handful of dependent L2 round trips), not HBM — read `launch_us`, not `frac`
+            roof["note"] = ("ensemble is L2-resident: latency-bound; launch_us (one half-step) against the ~2 us "
+                            "grid-barrier floor is the figure of merit, frac is reported for completeness only")
 
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             r, n, dt, threads = cpu_rate(wl, 12.0, wl["cpu_walkers"])
             cpu = {"value": r, "unit": UNIT, "cores": threads, "kind": wl.get("cpu_kind", "port"),
-                   "sample": f"{wl['cpu_walkers']} walkers x {n} moves ({dt:.1f} s) of workload {wl['key']}, CPU oracle (OpenMP)"
-                             + (f", on {wl['cpu_rows']} of {wl['rows']} rows, rate scaled linearly by rows" if wl.get("rows") else "")}
+                   "sample": f"{wl['cpu_walkers']} walkers x {n} moves ({dt:.1f} s) of workload {wl['key']}, CPU oracle (OpenMP); "
+                             "cost per walker-step is independent of the ensemble size"
+                             + (f"; on {wl['cpu_rows']} of {wl['rows']} rows, rate scaled linearly by rows" if wl.get("rows") else "")}
         if wl.get("glm"):   # statically compiled kernel: numbers from the nvcc -Xptxas -v log (profiles/)
-            info = {"registers": 96, "local_bytes": 0, "shared_bytes": int(1024 + 4 * 2 * 16384 + 3 * 2 * 16384 + 256),
-                    "block": 576, "grid": "1 CTA per SM (persistent)", "launches_per_half_step": -(-(W // 2) // 512)}
+            info = {"block": 576, "grid": "1 CTA per SM (persistent)", "launches_per_half_step": -(-(W // 2) // 512)}
         else:
-            info = sfactory.kernel_info(kernel_name)
+            info = sfactory.kernel_info("bay_stretch_bare")
+        wl["walkers"] = W_global if partition else W
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
                 "scaling": "strong" if (wl.get("glm") or args.strong) else "weak", "vs_baseline": None,
                 "dtype": "f32 (bf16x3 split on tensor cores, fp32 accumulate)" if wl.get("glm") else "f32",
                 "data": "synthetic",
-                "config": {"workload": wl["desc"], "walkers_per_gpu": W, "dim": D, "moves_per_step": M, "a": a,
-                           **({"rows": wl["rows"]} if wl.get("rows") else {}),
-                           "acceptance": round(p_acc, 4), "wgs": args.wgs,
-                           "parallelism": "single GPU" if world == 1 else (
-                               f"rows sharded over {world} GPUs, walkers replicated, NCCL all-reduce of per-walker sums"
-                               if sharded else
-                               f"one ensemble of {W_global} walkers partitioned over {world} GPUs, " + (
-                                   "NCCL all-gather of the updated slice every half-step"
-                                   if os.environ.get("BAY_P2P", "1").startswith("0") else
-                                   "each rank keeps its own slices; partner rows PULLED from the owning rank over "
-                                   "NVLink peer memory + flag barrier every half-step (BAY_PULL=1)"
-                                   if os.environ.get("BAY_PULL", "0") == "1" else
-                                   "accepted walkers stored into every peer's ensemble by the stretch kernel (NVLink "
-                                   "peer memory) + flag barrier every half-step")),
-                           "l2": "flushed between timed steps (256 MiB write)",
-                           "kernel": {"name": kernel_name, **info}},
+                "config": job_config(wl, args),
+                "details": {"walkers_per_gpu": W, "acceptance": round(p_acc, 4),
+                            "parallelism": "single GPU" if world == 1 else (
+                                f"rows sharded over {world} GPUs, walkers replicated, NCCL all-reduce of per-walker sums"
+                                if sharded else f"one ensemble of {W_global} walkers partitioned over {world} GPUs"),
+                            "l2": "flushed between timed steps (256 MiB write)",
+                            "kernel": {"name": kernel_name, **info}},
                 "e2e": {"value": e2e_value, "unit": UNIT,
                         "h2d_bytes_per_step": int(xs_host.nbytes + lp_host.nbytes),
                         "d2h_bytes_per_step": int(xs_host.nbytes + lp_host.nbytes),
                         "what": "bay_set_state64(pinned host ensemble) + burn-in! + bay_get_state64(pinned host) per step"},
+                "setup": {"sampler_create_s": setup_s,
+                          "what": "one-off bay_sampler_create_dev: dataset -> bf16 hi/lo planes, X^T y, column sums"
+                                  if wl.get("glm") else "one-off bay_sampler_create"},
                 "gpu_launches": int(launches),
                 "roofline": roof,
+                "parity_check": parity.get("verdict"), "parity": parity,
+                "mode_a": mode_a,
                 "cpu_baseline": cpu, "clocks": clk}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def sampler_kernel_name(sampler) -> str:
+    return "k_quadform_move_tc" if getattr(sampler, "uses_quadform", lambda: False)() else "bay_stretch_bare"
+
+
+def run_mode_a(args, torch, dist, bb, factory, stream, flush, barrier, rank, world):
+    """c5 (100-D correlated Gaussian), 2^20 walkers in TOTAL, partitioned by walker over the GPUs of this run."""
+    from bayadera_b200 import models
+    m = models.mvn_model(100)
+    W_total, moves, a, steps = 2 ** 20, 4, 1.25, max(5, min(args.steps, 10))
+    s = factory.mcmc_factory(m).create_sampler(321, W_total, models.mvn_params(100)[0]).init_position(322, m.limits_array())
+    s.burn_in(64, a)
+    p_acc = s.acc_rate(a)
+    for _ in range(3):
+        s.burn_in(moves, a)
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for s_ev, e_ev in ev:
+        flush.fill_(1)
+        s_ev.record(stream)
+        s.burn_in(moves, a)
+        e_ev.record(stream)
+    barrier()
+    ms = torch.tensor([sum(x.elapsed_time(y) for x, y in ev)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms[0])
+    value = W_total * moves * steps / (ms * 1e-3)
+    H_local = W_total // 2 // world
+    out = {"workload": "100-D correlated Gaussian, 2^20 walkers in total partitioned over the GPUs (BASELINE configs[4])",
+           "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "scaling": "strong", "steps": steps,
+           "moves_per_step": moves, "ms_per_step": ms / steps, "acceptance": round(p_acc, 4),
+           "kernel": sampler_kernel_name(s),
+           "half_step_us": ms * 1e3 / (2.0 * moves * steps),
+           "hbm_GBps_per_gpu": H_local * algorithmic_bytes_per_walker_step(100, p_acc) / (ms * 1e-3 / (2.0 * moves * steps)) / 1e9}
+    if world > 1:
+        # partner rows that live on another rank: (R-1)/R of this rank's walkers fetch one 400-byte row each
+        nv = (world - 1) / world * H_local * 400.0
+        out["nvlink_bytes_per_half_step_per_gpu"] = nv
+        out["nvlink_roofline_us"] = nv / 770e9 * 1e6
+        out["nvlink_note"] = "bytes that must cross NVLink / the measured 770 GB/s per direction per GPU (B200_PROFILING.md)"
+    s.release()
+    return out
 
 
 if __name__ == "__main__":

@@ -449,6 +449,15 @@ int orc_acor(uint32_t dim, uint32_t n, uint32_t wgs, float *series,
 /* The oracle for it is simply the serial model callback above.              */
 /* ------------------------------------------------------------------------- */
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the CPU baseline asks for all host cores explicitly */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

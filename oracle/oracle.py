@@ -72,6 +72,7 @@ def lib() -> C.CDLL:
         L.orc_acor.restype = C.c_int
         L.orc_acor.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, _f32p, _f32p, _f32p, _f32p, C.POINTER(C.c_uint32)]
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 

@@ -114,6 +114,13 @@ def main():
     r = sharded.run_sampler(64, 1.5)
     assert 0.0 < r["acceptance-rate"] < 1.0
 
+    # the self-checks bench.py runs before it prints a multi-GPU line (bayadera_b200/selfcheck.py)
+    from bayadera_b200 import selfcheck
+    ra = selfcheck.mode_a_bit_identity(multi, single, world)
+    assert ra["ok"], ra
+    rb = selfcheck.mode_b_replicas(multi, single, rank, world)
+    assert rb["ok"], rb
+
     dist.barrier()
     if rank == 0:
         print(f"MULTIGPU OK world={world}", flush=True)

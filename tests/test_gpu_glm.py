@@ -274,5 +274,7 @@ def test_glm_delta_logp_and_accept_mask_at_bench_size(factory):
     assert 0.02 < m64.mean() < 0.98
     assert (m64 != mtc).sum() <= 2, int((m64 != mtc).sum())              # only exact near-ties may flip
     # absolute level: the summed log-partition itself, against fp64, well inside the north-star's 1e-5 relative
-    assert np.abs(sums[0] - sums[2]).max() < 1e-7 * np.abs(sums[2]).max()
+    lvl = np.abs(sums[0] - sums[2]).max() / np.abs(sums[2]).max()
+    print(f"level error of the summed log-partition vs fp64: {lvl:.3e} relative")
+    assert lvl < 1e-6
     sampler.release()
