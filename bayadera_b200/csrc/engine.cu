@@ -717,6 +717,7 @@ extern "C" int bay_model_release(bay_model* m) {
 
 extern "C" int bay_model_kernel_info(bay_model* m, const char* kernel, int* regs, int* local_bytes, int* smem_bytes) {
     if (!m || !kernel) return fail(BAY_EINVAL, "NULL argument");
+    USE_ENGINE(m->e);
     CUfunction f = nullptr;
     CUresult cr = g_cu.ModuleGetFunction(&f, m->cvar_state == 1 ? m->cmod : m->mod, kernel);   // the variant samplers run
     if (cr != CUDA_SUCCESS) return cu_fail(cr, kernel);
@@ -953,6 +954,8 @@ static int sampler_create_common(bay_model* m, int32_t seed, int64_t walkers, in
 extern "C" int bay_sampler_create(bay_model* m, int32_t seed, int64_t walkers, const float* params_host,
                                   int64_t params_count, bay_sampler** out) {
     if (params_count > 0 && !params_host) return fail(BAY_EINVAL, "params_host is NULL");
+    if (!m) return fail(BAY_EINVAL, "NULL model");
+    USE_ENGINE(m->e);
     bay_sampler* s = nullptr;
     TRY(sampler_create_common(m, seed, walkers, params_count, &s));
     const size_t bytes = sizeof(float) * (size_t)(params_count > 0 ? params_count : 1);
@@ -976,6 +979,8 @@ extern "C" int bay_sampler_create(bay_model* m, int32_t seed, int64_t walkers, c
 
 extern "C" int bay_sampler_create_dev(bay_model* m, int32_t seed, int64_t walkers, uint64_t params_dev,
                                       int64_t params_count, bay_sampler** out) {
+    if (!m) return fail(BAY_EINVAL, "NULL model");
+    USE_ENGINE(m->e);
     bay_sampler* s = nullptr;
     TRY(sampler_create_common(m, seed, walkers, params_count, &s));
     s->params = reinterpret_cast<float*>(params_dev);

@@ -78,17 +78,21 @@ def logreg_rows_host(rows: int, d: int, seed: int = 2024) -> np.ndarray:
 
 
 def logreg_rows_device(torch, rows: int, d: int, seed: int, device):
-    """Same distribution generated on the device (nothing shipped over PCIe for the 2.6 GB matrix)."""
+    """Same distribution generated on the device (nothing shipped over PCIe for the 2.6 GB matrix).  `seed` draws
+    the rows (a different stream per row shard); the generating coefficients theta* are the same on every rank, so
+    the union of the shards is ONE logistic-regression dataset.  Returns (params vector, theta*)."""
+    gt = torch.Generator(device=device)
+    gt.manual_seed(2024)
+    theta = torch.randn(d, generator=gt, device=device) / (8.0 ** 0.5)
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     out = torch.empty(rows * (d + 1) + 1, dtype=torch.float32, device=device)
     mat = out[:-1].view(rows, d + 1)
     mat[:, 1:].normal_(generator=g)
-    theta = torch.randn(d, generator=g, device=device) / (8.0 ** 0.5)
     p = torch.sigmoid(mat[:, 1:] @ theta)
     mat[:, 0] = (torch.rand(rows, generator=g, device=device) < p).float()
     out[-1] = 1.0 / 200.0
-    return out
+    return out, theta.double().cpu().numpy()
 
 
 def algorithmic_bytes_per_walker_step(dim: int, p_acc: float) -> float:
@@ -334,13 +338,15 @@ def main():
         init_engine_comm(factory, rank, world, torch.device("cuda", local_rank))
     sfactory = factory.mcmc_factory(model)
     params = wl["params"]
+    theta_star = None
     if params is None:
         if sharded:
             b, e = shard_rows(wl["rows"], world, rank)
-            local_rows, seed = e - b, 2024 + 1000 * rank
+            local_rows, seed = e - b, 2025 + 1000 * rank
         else:
-            local_rows, seed = wl["rows"], 2024
-        params = bb.DeviceParams.from_torch(logreg_rows_device(torch, local_rows, D, seed, torch.device("cuda", local_rank)))
+            local_rows, seed = wl["rows"], 2025
+        rows_dev, theta_star = logreg_rows_device(torch, local_rows, D, seed, torch.device("cuda", local_rank))
+        params = bb.DeviceParams.from_torch(rows_dev)
     # every rank drives the same (replicated or partitioned) ensemble: identical seeds everywhere
     if partition and args.strong:
         W = max(W // world // (2 * args.wgs), 1) * 2 * args.wgs     # this GPU's share of the config's ensemble
@@ -400,11 +406,12 @@ def main():
     if not args.no_parity_check:
         from bayadera_b200 import selfcheck
         if wl.get("glm"):
-            # the timed sampler itself, at the full dataset: Δlogp of stretch proposals around the current ensemble
-            # mean, tensor-core path against the fp64 traversal of the same rows (all-reduced over the row shards)
-            centre = xs0.astype(np.float64).mean(axis=0)
-            spread = float(xs0.astype(np.float64).std(axis=0).mean())
-            parity["glm_dlogp_vs_fp64"] = selfcheck.glm_delta_logp(sampler, centre, max(spread, 1e-6), pairs=128, a=a)
+            # the timed sampler itself, at the full dataset: Δlogp of stretch proposals between points scattered at the
+            # posterior's own scale (sd ~ 1/sqrt(0.2 rows)) around the generating coefficients — where the accept
+            # test consumes O(1)..O(10) differences of ~7e6 sums — tensor-core path against the fp64 traversal of
+            # the same rows (all-reduced over the row shards)
+            parity["glm_dlogp_vs_fp64"] = selfcheck.glm_delta_logp(sampler, theta_star, (0.2 * wl["rows"]) ** -0.5,
+                                                                   pairs=128, a=a)
         if world > 1:
             single = bb.B200BayaderaFactory(device=local_rank, stream=stream.cuda_stream, wgs=args.wgs)
             parity["mode_a_partition_vs_1gpu"] = selfcheck.mode_a_bit_identity(factory, single, world)

@@ -4,7 +4,7 @@
 tag=${1:-run}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${tag}_smi.txt 2>&1
-(time python -m pytest tests -m gpu -x -q --durations=15) > gpurun_out/${tag}_pytest.log 2>&1
+(time python -m pytest tests -m gpu -q --durations=15) > gpurun_out/${tag}_pytest.log 2>&1
 echo "pytest exit=$?" >> gpurun_out/${tag}_pytest.log
 tail -5 gpurun_out/${tag}_pytest.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; tail -2 gpurun_out/${tag}_smoke.log
