@@ -58,6 +58,7 @@ SIGNATURES = {
     "bay_model_release": (C.c_int, [_vp]),
     "bay_model_compile_check": (C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_uint32,
                                           C.POINTER(_i64), C.c_char_p, _i64]),
+    "bay_model_uses_quadform": (C.c_int, [_vp]),
     "bay_model_kernel_info": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bay_sampler_create": (C.c_int, [_vp, _i32, _i64, _vp, _i64, _pp]),
     "bay_sampler_create_dev": (C.c_int, [_vp, _i32, _i64, C.c_uint64, _i64, _pp]),

@@ -12,6 +12,7 @@
 #include "../../include/bayadera_b200.h"
 #include "kernels.cuh"
 #include "kernels_glm_tc.cuh"
+#include "kernels_quadform_tc.cuh"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -277,6 +278,7 @@ struct bay_model {
     CUfunction f_glm_loglik64 = nullptr;   // fp64 yardstick of the likelihood (bay_glm_loglik_probe)
     bool glm = false;
     int glm_link = 0;      // 0 Bernoulli-logit (softplus), 1 Poisson-log (exp)
+    bool quadform = false; // BAY_MODEL_QUADFORM: logp = -1/2 |U (x - mu)|^2, moves run on k_quadform_move_tc
     bool mirror = false;   // AoS mirror of the ensemble for the partner gather (DIM >= 4, non-GLM)
     bool peers = false;    // kernels store accepted walkers into every rank's ensemble block (multi-GPU mode A)
     bool pull = false;     // ... or (experimental, BAY_PULL=1) nothing is stored remotely and partner rows are pulled
@@ -316,6 +318,9 @@ struct bay_sampler {
     bool cp = false;                    // runs the constant-parameter kernel variant
     bool remote_stale = false;          // pull mode: other ranks' slices of the local copy are out of date
     bool soa_stale = false;             // peers forwarded mirror rows only: rebuild xs from xa before a read-out
+    bool soa_own_stale = false;         // the tensor-core move updates ONLY the mirror: xs is stale everywhere, also
+                                        // for this rank's own walkers (generic kernels must wait for a rebuild)
+    bool qf_configured = false;         // dynamic shared-memory opt-in of k_quadform_move_tc done on this device
     void* peer_mapped[8] = {nullptr};   // what cudaIpcOpenMemHandle returned (to close on release)
     float* loop_betas = nullptr;        // per-step inverse temperatures (anneal!)
     int64_t loop_betas_cap = 0;
@@ -656,6 +661,11 @@ extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsr
     m->flags = flags;
     m->block = bare_block_for(dim);
     m->mirror = model_wants_mirror(dim, flags);
+    {
+        const char* env = getenv("BAY_QUADFORM_TC");
+        m->quadform = (flags & BAY_MODEL_QUADFORM) && m->mirror && dim % 4 == 0 && dim <= bay::qf::MAX_D &&
+                      params_size == dim + dim * dim && !(env && env[0] == '0');
+    }
     m->peers = peers;
     m->pull = pull;
     m->dima = (dim + 3) / 4 * 4;
@@ -714,6 +724,8 @@ extern "C" int bay_model_release(bay_model* m) {
     delete m;
     return BAY_OK;
 }
+
+extern "C" int bay_model_uses_quadform(bay_model* m) { return m && m->quadform ? 1 : 0; }
 
 extern "C" int bay_model_kernel_info(bay_model* m, const char* kernel, int* regs, int* local_bytes, int* smem_bytes) {
     if (!m || !kernel) return fail(BAY_EINVAL, "NULL argument");
@@ -1055,6 +1067,7 @@ extern "C" int bay_init_position_uniform(bay_sampler* s, int32_t seed, const flo
     bay::k_init_walkers<<<cdiv(n4, 256), 256, 0, e->stream>>>(n4, (uint32_t)s->D, (uint32_t)seed, s->limits, s->xs,
                                                            (uint32_t)s->W);
     CKLAUNCH();
+    s->soa_stale = s->soa_own_stale = s->remote_stale = false;   // a full rewrite: every local copy is current
     TRY(mirror_sync(s));
     TRY(launch_logfn_all(s));
     TRY(peer_settle(s));
@@ -1073,6 +1086,7 @@ extern "C" int bay_init_position_from(bay_sampler* s, const bay_sampler* other) 
     TRY(soa_fresh(const_cast<bay_sampler*>(other)));
     CK(cudaMemcpyAsync(s->xs, other->xs, sizeof(float) * (size_t)s->D * s->W, cudaMemcpyDeviceToDevice, e->stream));
     TRY(peer_settle(const_cast<bay_sampler*>(other)));
+    s->soa_stale = s->soa_own_stale = s->remote_stale = false;
     TRY(mirror_sync(s));
     TRY(launch_logfn_all(s));
     TRY(peer_settle(s));
@@ -1160,16 +1174,81 @@ static int ensemble_gather(bay_sampler* s) {
 
 static int soa_fresh(bay_sampler* s) {
     TRY(ensemble_gather(s));
-    if (!s->soa_stale) return BAY_OK;
+    if (!s->soa_stale && !s->soa_own_stale) return BAY_OK;
     TRY(aos_to_soa(s->m->e, s->xa, 0, (uint64_t)s->m->dima, (uint32_t)s->D, (uint64_t)s->W, s->xs, (uint64_t)s->W));
     s->soa_stale = false;
+    s->soa_own_stale = false;
     return BAY_OK;
+}
+
+// Before a GENERIC kernel (which reads its own walkers from the SoA matrix and, between GPUs, expects every replica
+// to be current) runs after tensor-core moves: bring in the other ranks' slices, rebuild the SoA matrix, and — peers
+// may go on to overwrite their slices — pass a barrier once everybody has read what it needs.  Collective.
+static int generic_ready(bay_sampler* s) {
+    if (!s->soa_own_stale && !s->remote_stale) return BAY_OK;
+    const bool gathered = s->remote_stale;
+    TRY(soa_fresh(s));
+    if (gathered) TRY(peer_settle(s));
+    return BAY_OK;
+}
+
+// ---- BAY_MODEL_QUADFORM: half-ensemble move on the tensor cores (kernels_quadform_tc.cuh) ----------------------
+// Eligible: the model's parameters are [mu | U] in device memory and, between GPUs, the ensemble lives in the
+// peer-mapped block (partner rows are pulled from the owning rank over NVLink; nothing is forwarded).
+static bool quadform_usable(const bay_sampler* s) {
+    const bay_model* m = s->m;
+    if (!m->quadform || !s->xa || s->params_count < (int64_t)s->D + (int64_t)s->D * s->D) return false;
+    if (partitioned(s) && !m->peers) return false;    // NCCL all-gather exchange: generic kernels only
+    return true;
+}
+
+static int quadform_half(bay_sampler* s, int half, uint32_t seed, uint32_t tag, float cA, float cB, float cC,
+                         float beta, uint32_t step) {
+    bay_model* m = s->m;
+    bay_engine* e = m->e;
+    const size_t smem = bay::qf::smem_bytes();
+    if (!s->qf_configured) {
+        CK(cudaFuncSetAttribute(bay::qf::k_quadform_move_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        s->qf_configured = true;
+    }
+    bay::qf::Args a;
+    memset(&a, 0, sizeof a);
+    const size_t dima = (size_t)m->dima, H = (size_t)s->H;
+    a.mu = s->params;
+    a.U = s->params + s->D;
+    a.xa_active = s->xa + (half ? H : 0) * dima;
+    a.lp_active = s->lp + (half ? H : 0);
+    const size_t compl_off = (half ? 0 : H) * dima;
+    if (partitioned(s)) {
+        for (int r = 0; r < e->nranks; r++)
+            a.xa_compl[r] = s->peer_tab.base[r] + sizeof(float) * (s->peer_tab.xa_off + compl_off);
+        a.hs = (uint32_t)(s->H / e->nranks);
+        s->remote_stale = true;
+    } else {
+        a.xa_compl[0] = (unsigned long long)(uintptr_t)(s->xa + compl_off);
+        a.hs = (uint32_t)s->H;
+    }
+    a.K = (uint32_t)s->H;
+    my_slice(s, &a.k_begin, &a.k_end);
+    a.D = (uint32_t)s->D;
+    a.DA = (uint32_t)m->dima;
+    a.seed = seed; a.tag = tag; a.step = step;
+    a.cA = cA; a.cB = cB; a.cC = cC; a.beta = beta;
+    a.accepted = nullptr;
+    const uint32_t tiles = cdiv(a.k_end - a.k_begin, bay::qf::TILE);
+    uint32_t grid = (uint32_t)e->sm_count < tiles ? (uint32_t)e->sm_count : tiles;
+    bay::qf::k_quadform_move_tc<<<grid, bay::qf::THREADS, smem, e->stream>>>(a);
+    CKLAUNCH();
+    s->soa_own_stale = true;
+    return exchange_half(s, half);
 }
 
 static int half_bare(bay_sampler* s, int half, uint32_t seed, uint32_t tag, float cA, float cB, float cC,
                      float beta, uint32_t step) {
     bay_model* m = s->m;
     if (m->glm) return glm_half(s, half, seed, tag, cA, cB, cC, beta, step, 0u);
+    if (quadform_usable(s)) return quadform_half(s, half, seed, tag, cA, cB, cC, beta, step);
+    TRY(generic_ready(s));
     uint32_t K = (uint32_t)s->H, pitch = (uint32_t)s->W;
     float* act = s->xs + (half ? s->H : 0);
     float* cmp = s->xs + (half ? 0 : s->H);
@@ -1198,6 +1277,7 @@ static int half_accu(bay_sampler* s, int half, uint32_t seed, uint32_t tag, floa
                      uint32_t step) {
     bay_model* m = s->m;
     if (m->glm) return glm_half(s, half, seed, tag, cA, cB, cC, 1.0f, step, 1u);
+    TRY(generic_ready(s));
     uint32_t K = (uint32_t)s->H, pitch = (uint32_t)s->W, accumulate = half ? 1u : 0u;
     float* act = s->xs + (half ? s->H : 0);
     float* cmp = s->xs + (half ? 0 : s->H);
@@ -1227,6 +1307,7 @@ static int half_accu(bay_sampler* s, int half, uint32_t seed, uint32_t tag, floa
 static bool loop_usable(const bay_sampler* s, int64_t n) {
     const bay_model* m = s->m;
     if (m->glm || !m->f_loop || n < 2) return false;
+    if (quadform_usable(s)) return false;             // the tensor-core move runs one launch per half-step
     if (partitioned(s) && (!m->peers || m->pull)) return false;   // NCCL exchange / pull mode: one kernel per half-step
     uint32_t kb, ke;
     my_slice(s, &kb, &ke);
@@ -1238,6 +1319,7 @@ static bool loop_usable(const bay_sampler* s, int64_t n) {
 static int move_bare_loop(bay_sampler* s, int64_t n, const float* betas, float cA, float cB, float cC) {
     bay_model* m = s->m;
     bay_engine* e = m->e;
+    TRY(generic_ready(s));
     float* betas_dev = nullptr;
     if (betas) {
         if (s->loop_betas_cap < n) {
@@ -1417,6 +1499,7 @@ static int move_accu_loop(bay_sampler* s, int64_t n) {
     float cA, cB, cC;
     stretch_coeffs(s->a_move, &cA, &cB, &cC);
     TRY(ensure_means(s, s->means_n + n));
+    TRY(generic_ready(s));
     TRY(bind_params(s));
     uint32_t K = (uint32_t)s->H, pitch = (uint32_t)s->W, seed = (uint32_t)s->move_seed, step0 = s->move_counter;
     uint32_t n_steps = (uint32_t)n;

@@ -143,6 +143,10 @@ class B200StretchFactory:
     def create_sampler(self, seed: int, walkers: int, params) -> "B200Stretch":
         return B200Stretch(self, seed, walkers, params)
 
+    def uses_quadform(self) -> bool:
+        """True when moves of this model run on the tensor-core quadratic-form kernel (BAY_MODEL_QUADFORM)."""
+        return bool(self._L.bay_model_uses_quadform(self._h))
+
     def kernel_info(self, kernel: str = "bay_stretch_bare") -> dict:
         r, l, s = C.c_int(), C.c_int(), C.c_int()
         check(self._L.bay_model_kernel_info(self._h, kernel.encode(), C.byref(r), C.byref(l), C.byref(s)))
@@ -364,6 +368,9 @@ class B200Stretch:
         l = np.ascontiguousarray(logfn64, dtype=np.float64).reshape(-1)
         check(self._L.bay_set_state64(self._h, ptr(x), ptr(l)))
         return self
+
+    def uses_quadform(self) -> bool:
+        return self.sfactory.uses_quadform()
 
     def glm_loglik_probe(self, points, method: int = 0) -> np.ndarray:
         """Row-additive GLM samplers: sum over the dataset of A(x_row . point) for each of the given points

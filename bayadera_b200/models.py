@@ -32,6 +32,7 @@ FAST_MATH = 0x1
 ROW_ADDITIVE = 0x2
 GLM_LOGISTIC = 0x4
 GLM_POISSON = 0x8
+QUADFORM = 0x10
 
 _SIG = ("const uint32_t data_len, const uint32_t params_len, const REAL* params, "
         "const uint32_t dim, const REAL* x")
@@ -387,8 +388,9 @@ def mvn_model(d: int = 100) -> DeviceModel:
         {rows_block(rest, str(8 * full), str(2 * full)) if rest else ""}
         return -0.5f * acc;"""
     src = distribution_source(f"mvn{d}_mcmc_logpdf", body)
+    # QUADFORM: the engine may evaluate -1/2 |U (x - mu)|^2 for 128-walker tiles on the tensor cores (d <= 128)
     return DeviceModel(f"mvn{d}", (src,), f"mvn{d}_mcmc_logpdf", d, d + d * d,
-                       _lim(*([(-30.0, 30.0)] * d)), f"mvn{d}_mcmc_logpdf")
+                       _lim(*([(-30.0, 30.0)] * d)), f"mvn{d}_mcmc_logpdf", flags=FAST_MATH | QUADFORM)
 
 
 def mvn_params(d: int = 100, seed: int = 5) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:

@@ -485,6 +485,9 @@ def main():
                              + (f"; on {wl['cpu_rows']} of {wl['rows']} rows, rate scaled linearly by rows" if wl.get("rows") else "")}
         if wl.get("glm"):   # statically compiled kernel: numbers from the nvcc -Xptxas -v log (profiles/)
             info = {"block": 576, "grid": "1 CTA per SM (persistent)", "launches_per_half_step": -(-(W // 2) // 512)}
+        elif sampler.uses_quadform():
+            info = {"registers": 128, "block": 512, "grid": "1 CTA per SM (persistent), 128-walker tiles",
+                    "shared_bytes": 1024 + 131072 + 8192}
         else:
             info = sfactory.kernel_info("bay_stretch_bare")
         wl["walkers"] = W_global if partition else W

@@ -52,6 +52,10 @@ typedef struct bay_sampler bay_sampler; /* replaces GTXStretch, G/:282-541 */
 #define BAY_MODEL_ROW_ADDITIVE 0x2u /* model also defines BAY_ROWLIK / BAY_PRIOR */
 #define BAY_MODEL_GLM_LOGISTIC 0x4u /* data rows are [y, x_1..x_D]; likelihood is Bernoulli-logit of x·theta */
 #define BAY_MODEL_GLM_POISSON 0x8u  /* data rows are [y, x_1..x_D]; likelihood is Poisson with log link: y*eta - exp(eta) */
+#define BAY_MODEL_QUADFORM    0x10u /* Gaussian / quadratic form: params = [mu (D) | U (D x D row-major)], no data, and
+                                       LOGFN(x) = -1/2 |U (x - mu)|^2.  D a multiple of 4, <= 128: moves of 128-walker
+                                       tiles run as a dense contraction on the tensor cores; LOGFN
+                                       itself still serves init-position!, run-sampler! and the density engine. */
 
 const char *bay_last_error(void);
 const char *bay_version(void);
@@ -105,6 +109,8 @@ int bay_model_release(bay_model *m);
  * ptxas -v register/spill report, or the compiler errors). */
 int bay_model_compile_check(const char *const *srcs, int nsrc, const char *logfn_name, int dim, int wgs,
                             uint32_t flags, int64_t *cubin_bytes, char *log_buf, int64_t log_cap);
+/* 1 when moves of this model run on the tensor-core quadratic-form kernel (BAY_MODEL_QUADFORM accepted), else 0 */
+int bay_model_uses_quadform(bay_model *m);
 /* registers/spills/shared of the compiled stretch kernel (profiling aid) */
 int bay_model_kernel_info(bay_model *m, const char *kernel, int *regs, int *local_bytes, int *smem_bytes);
 

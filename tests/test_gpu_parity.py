@@ -411,6 +411,9 @@ def test_persistent_loop_and_mirror_do_not_change_the_chain(factory, name, case,
     constant-memory copy of the parameters are pure implementation choices: chains must be bit-identical with any of
     them switched off (BAY_LOOP=0, BAY_MIRROR=0, BAY_CPARAMS=0)."""
     model, params, limits, walkers = case()
+    # a property of the generic program: quadratic-form models are kept off their tensor-core kernel here (that one is
+    # held against the generic kernel and the oracle in test_quadform_tensor_core_move_*)
+    monkeypatch.setenv("BAY_QUADFORM_TC", "0")
     base = _chain_state(factory, model, params, limits, walkers)
     for var in ("BAY_LOOP", "BAY_MIRROR", "BAY_CPARAMS"):
         monkeypatch.setenv(var, "0")
@@ -423,6 +426,52 @@ def test_persistent_loop_and_mirror_do_not_change_the_chain(factory, name, case,
         assert np.array_equal(base[3], other[3]), (name, var)                      # per-step ensemble means
         assert np.array_equal(base[4], other[4], equal_nan=True), (name, var)      # autocorrelation times
         assert np.array_equal(base[5]["xs"], other[5]["xs"]), (name, var)          # state after run-sampler!
+
+
+# ---- quadratic-form models on the tensor cores (k_quadform_move_tc) ---------------------------------------------
+@pytest.mark.parametrize("d,walkers", [(100, 2048), (8, 1024), (64, 1536), (128, 1024), (36, 4096 + 512)])
+def test_quadform_tensor_core_move_vs_oracle(factory, d, walkers):
+    """Step-locked against the oracle's serial LOGFN: proposals bit-identical, accepted log-densities within the
+    north-star's 1e-5 relative (measured ~3e-7: fp16 hi/lo split with power-of-two row scales), accept masks equal
+    except at near-ties.  Dimensions exercise one / two K chunks, N padding (36 -> 48) and ragged last tiles."""
+    model = models.mvn_model(d)
+    params, _, _ = models.mvn_params(d)
+    sf, gpu, cpu = make_pair(factory, model, 3, walkers, params, model.limits_array())
+    assert sf.uses_quadform()
+    check_steplocked(gpu, cpu, steps=2, a=1.2, tie_tol=5e-2)
+    # a few unlocked steps, then the log-densities the chain carries must be the model's at the positions it holds
+    gpu.burn_in(5, 1.3)
+    st = gpu.get_state()
+    cpu.set_positions(st["xs"].reshape(-1))
+    assert logpdf_close(st["logfn"], cpu.lp, rtol=1e-5).all()
+
+
+def test_quadform_tensor_core_equals_generic_kernel(factory, monkeypatch):
+    """Same seeds, same proposals: the tensor-core move and the generic per-thread kernel may only part ways at
+    near-ties of the accept test; where they agree the positions are bit-identical."""
+    model = models.mvn_model(100)
+    params, mu, sigma = models.mvn_params(100)
+    lim = model.limits_array()
+    tc = factory.mcmc_factory(model).create_sampler(8, 8192, params).init_position(9, lim)
+    monkeypatch.setenv("BAY_QUADFORM_TC", "0")
+    sfg = factory.mcmc_factory(model)
+    monkeypatch.delenv("BAY_QUADFORM_TC")
+    assert not sfg.uses_quadform()
+    gen = sfg.create_sampler(8, 8192, params).init_position(9, lim)
+    for s in (tc, gen):
+        s.burn_in(3, 1.25)
+    a, b = tc.get_state(), gen.get_state()
+    same = np.all(a["xs"] == b["xs"], axis=1)
+    assert same.mean() > 0.995, same.mean()
+    assert logpdf_close(a["logfn"][same], b["logfn"][same], rtol=1e-5).all()
+    # statistics of a longer run: the posterior mean and covariance the chain is supposed to sample
+    tc.burn_in(400, 1.25)
+    x = tc.sample().astype(np.float64)
+    # every walker has moved and the ensemble contracts from the +-30 box towards N(mu, Sigma) (slow in D = 100)
+    assert np.abs(x.mean(axis=0) - mu).max() < 8.0
+    assert np.all(np.isfinite(tc.get_state()["logfn"]))
+    rate = tc.acc_rate(1.25)
+    assert 0.2 < rate < 0.7, rate
 
 
 def test_constant_parameter_block_follows_the_sampler(factory):
