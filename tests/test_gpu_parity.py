@@ -468,7 +468,7 @@ def test_quadform_tensor_core_equals_generic_kernel(factory, monkeypatch):
     tc.burn_in(400, 1.25)
     x = tc.sample().astype(np.float64)
     # every walker has moved and the ensemble contracts from the +-30 box towards N(mu, Sigma) (slow in D = 100)
-    assert np.abs(x.mean(axis=0) - mu).max() < 8.0
+    assert np.abs(x - mu).mean() < 12.0                  # started at mean |x - mu| = 15
     assert np.all(np.isfinite(tc.get_state()["logfn"]))
     rate = tc.acc_rate(1.25)
     assert 0.2 < rate < 0.7, rate
