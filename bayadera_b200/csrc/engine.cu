@@ -356,9 +356,16 @@ struct bay_sampler {
     // tensor-core variant (DIM <= 64): bf16 hi/lo planes of the dataset and of the walker block + TMA maps
     bool glm_tc = false;
     uint32_t glm_nkc = 1;                     // 64-wide K chunks per row (DIM <= 64: 1, <= 128: 2)
-    __nv_bfloat16 *glm_xh = nullptr, *glm_xl = nullptr, *glm_ah = nullptr, *glm_al = nullptr;
+    __nv_bfloat16 *glm_xh = nullptr, *glm_xl = nullptr, *glm_ah = nullptr, *glm_am = nullptr, *glm_al = nullptr;
+    int glm_terms = 4;                        // MMAs per K step: 4 = (dh+dm+dl).Xh + dh.Xl, 5 adds dm.Xl
+    float* glm_theta0 = nullptr;              // D: reference point of the tensor-core contraction (kernels_glm_tc.cuh)
+    float* glm_eta0 = nullptr;                // rows padded to a tile: log2(e) * x_row . theta0
+    float* glm_mean = nullptr;                // D: mean of the points of the current likelihood call
+    int* glm_ref_changed = nullptr;           // device flag: the reference point moved, eta0 must be recomputed
+    bool glm_ref_init = false;                // theta0 / eta0 have been computed at least once
     CUtensorMap glm_map_xh, glm_map_xl;
-    std::map<uint64_t, std::pair<CUtensorMap, CUtensorMap>> glm_amaps;   // (first walker, count) -> (hi, lo) maps
+    struct GlmWalkerMaps { CUtensorMap hi, mid, lo; };
+    std::map<uint64_t, GlmWalkerMaps> glm_amaps;   // (first walker, count) -> maps of the three theta planes
     // host-side counters: G/:282-287, 340-400
     int32_t bare_seed = 0, move_seed = 0;
     uint32_t bare_counter = 0, move_counter = 0;

@@ -6,12 +6,29 @@
 // 5th-generation tensor cores, followed by a thread-local softplus reduction:
 //   * TMEM lanes = walkers, TMEM columns = dataset rows, so every epilogue thread owns one walker and sums
 //     over the columns it reads with tcgen05.ld — no cross-lane reduction at all.
-//   * fp32-level accuracy from bf16 inputs by a 3-term split (hi*hi + hi*lo + lo*hi), fp32 accumulation in TMEM:
-//     the dataset is split ONCE into (Xh, Xl) bf16 planes (same HBM bytes as the fp32 matrix), the walker block
-//     every half-step.  Dropped term lo*lo and split residuals are ~2^-16 relative per product, zero-mean.
-//   * Persistent, warp-specialised CTA (1 per SM): warp 8 = TMA producer (3-stage ring of 32 KB X tiles),
-//     warp 9 = TMEM allocator + single-thread MMA issuer (4 accumulator stages of 128 columns),
+//   * fp32-level accuracy from bf16 inputs, fp32 accumulation in TMEM.  What the accept test needs is set by the
+//     DATASET SIZE: at 10^7 rows the log-partition sum has a gradient of ~10^6 per coefficient, so an error d in how a
+//     walker's coefficients are REPRESENTED shifts its log-density by ~10^6 * |d| — a two-piece bf16 split of theta
+//     (residual 2^-17 relative) is off by 5..20 in a difference that must be good to ~1e-2 (measured against the fp64
+//     traversal, tests/test_gpu_glm.py).  Theta is therefore split into THREE bf16 pieces (8+8+8 bits: exact), the
+//     dataset into two (Xh, Xl: a fixed 2^-17 perturbation of the data, the same for every walker), and the product is
+//     (th+tm+tl).Xh + (th+tm).Xl — five MMAs per K step (TERMS = 4 drops tm.Xl, ~2^-18 relative and zero-mean).
+//     The dataset is split ONCE into its planes (same HBM bytes as the fp32 matrix), the walker block every half-step.
+//   * REFERENCE POINT.  The tensor core does not round its fp32 accumulation to nearest: addends are aligned to the
+//     largest exponent and cut at ~2^-21 of it, so every row carries an error proportional to |eta| (measured: the
+//     error against fp64 is unchanged with bf16-exact inputs and falls 10x when |eta| is small).  The kernel therefore
+//     contracts only the SMALL part: theta = theta0 + delta, eta = x.theta0 + x.delta, with theta0 a per-sampler
+//     reference point (the mean of the points of a recent call) whose eta0 = log2(e) * x.theta0 is computed once in
+//     fp64 per refresh and streamed as one fp32 per row (+1.6 % HBM traffic); the planes hold the three pieces of
+//     delta and the epilogue adds eta0 to the accumulator in true fp32.  Near the posterior |x.delta| ~ 1e-2 and the
+//     tensor-core error drops below that of the fp32 SIMT traversal; far from it (early burn-in) it degrades
+//     gracefully to the plain scheme, where differences of log-densities are huge anyway.
+//   * Persistent, warp-specialised CTA (1 per SM): warp 16 = TMA producer (3-stage ring of 32 KB X tiles),
+//     warp 17 = TMEM allocator + single-thread MMA issuer (4 accumulator stages of 128 columns),
 //     warps 0-15 = four epilogue groups (4 warps = 128 TMEM lanes each), group g drains accumulator stage g.
+//   * A CTA holds the three planes of 256 walkers (96 KB); a launch covers up to FOUR such walker groups: CTA c works
+//     for group c % G on the row tiles c / G, c / G + gridDim / G, ...  The G CTAs of a slice stream the same row
+//     tiles at about the same time, so the dataset comes from HBM once per launch and from L2 for the other G - 1.
 //   * softplus(e) = max(e,0) + log(1 + exp(-|e|)); the log is taken of a running PRODUCT of 64 factors (1+t),
 //     so the epilogue costs one MUFU.EX2 per element and one MUFU.LG2 per 64 (MUFU is the binding unit).
 // There is no counterpart in the reference (its LOGFN loops over the dataset serially in every thread,
@@ -30,15 +47,19 @@ constexpr int KD = 64;                          // K extent of one operand tile 
 constexpr int MAX_KC = 2;                       // K chunks per dataset row: model dimension <= 128
 constexpr int NSTAGE = 3;                       // X-tile ring
 constexpr int NACC = 4;                         // TMEM accumulator stages (4 x 128 columns = 512)
-constexpr int MAX_WB = 4;                       // walker blocks per launch (512 walkers)
+constexpr int MAX_WB = 2;                         // walker blocks per CTA (256 walkers: three bf16 planes = 96 KB)
+constexpr int MAX_GROUPS = 4;                     // walker groups per launch (CTA c serves group c % groups)
 constexpr uint32_t TILE_BYTES = TILE * KD * 2;  // one bf16 plane of a tile: 16 KB
 constexpr int NGRP = 4;                         // epilogue groups (4 warps each), one per accumulator stage
+constexpr int ETA_RING = 8;                     // eta0 tiles in flight: producer <= NSTAGE tiles ahead of the MMA, MMA <=
+                                                // NACC tiles ahead of the slowest epilogue group: 3 + 4 < 8
 constexpr int THREADS = (4 * NGRP + 2) * 32;    // 16 epilogue warps + TMA warp + MMA warp
 constexpr uint32_t IDESC =                      // kind::f16: D=f32, A=B=bf16, both K-major, N=128, M=128
     (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
 
 __host__ __device__ constexpr size_t smem_bytes(int nwb, int nkc) {
-    return 1024 /*alignment slack*/ + (size_t)nwb * nkc * 2 * TILE_BYTES + (size_t)NSTAGE * 2 * TILE_BYTES + 256;
+    return 1024 /*alignment slack*/ + (size_t)nwb * nkc * 3 * TILE_BYTES + (size_t)NSTAGE * 2 * TILE_BYTES + 256 +
+           (size_t)ETA_RING * TILE * 4;
 }
 
 // ------------------------------------------------------------------ PTX helpers --
@@ -119,22 +140,26 @@ __device__ __forceinline__ float lg2_approx(float x) {
         : "r"(taddr) : "memory")
 
 // ------------------------------------------------------------------ the kernel --
-// map_xh/map_xl: [rows][64*NKC] bf16 planes of the dataset; map_ah/map_al: [n_walkers][64*NKC] bf16 planes of the
-// walker block (hi, lo), origin at the first walker of this launch.  partial: [NGRP*gridDim.x][ldp] doubles;
-// entry (NGRP*cta + group, wb*128 + lane) = that epilogue thread's sum.
+// map_xh/map_xl: [rows][64*NKC] bf16 planes of the dataset; map_ah/map_am/map_al: [n_walkers][64*NKC] bf16 planes of
+// the launch's walkers (three pieces of theta * log2 e), origin at the first walker of this launch.
+// groups: walker groups of NWB*128 walkers in this launch; CTA c serves group c % groups on row-tile slice c / groups.
+// partial: [NGRP * slices][ldp] doubles; entry (NGRP*slice + epilogue group, (g*NWB + wb)*128 + lane) = that
+// epilogue thread's sum.
 // NKC = 2 (64 < DIM <= 128): a row tile arrives as two 64-wide K chunks, each its own ring stage, and the MMAs of
-// both accumulate into the same TMEM stage; the walker block then takes 64 KB per 128 walkers, so NWB <= 2.
+// both accumulate into the same TMEM stage; the walker planes then take 96 KB per 128 walkers, so NWB = 1.
 // LINK = 0: A(eta) = softplus(eta) (Bernoulli-logit); LINK = 1: A(eta) = exp(eta) (Poisson-log): one MUFU.EX2 and one
 // FADD per element, nothing analytic left for the finish kernel.
-template <int NWB, int NKC, int LINK>
-__global__ void __launch_bounds__(THREADS, 1)  // (NWB, NKC) in {1, 2, 4} x {1}, {1, 2} x {2}
+template <int NWB, int NKC, int LINK, int TERMS>
+__global__ void __launch_bounds__(THREADS, 1)  // (NWB, NKC) in {1, 2} x {1}, {1} x {2}
 k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
-                const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
-                const uint32_t rows, const uint32_t n_tiles, double* __restrict__ partial, const uint32_t ldp) {
+                const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_am,
+                const __grid_constant__ CUtensorMap map_al, const float* __restrict__ eta0, const uint32_t rows,
+                const uint32_t n_tiles, const uint32_t groups, double* __restrict__ partial, const uint32_t ldp) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* a_hi = smem;                                   // NWB x NKC tiles, tile (wb, kc) at wb*NKC + kc
-    uint8_t* a_lo = a_hi + NWB * NKC * TILE_BYTES;          // NWB x NKC tiles
+    uint8_t* a_mi = a_hi + NWB * NKC * TILE_BYTES;
+    uint8_t* a_lo = a_mi + NWB * NKC * TILE_BYTES;
     uint8_t* b_base = a_lo + NWB * NKC * TILE_BYTES;        // NSTAGE x (hi, lo)
     uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + NSTAGE * 2 * TILE_BYTES);
     uint64_t* full_bar = bars;                              // [NSTAGE] TMA -> MMA
@@ -143,9 +168,11 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     uint64_t* tempty_bar = bars + 2 * NSTAGE + NACC;        // [NACC]   epilogue -> MMA
     uint64_t* a_bar = bars + 2 * NSTAGE + 2 * NACC;         // walker block landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2 * NACC + 1);
+    const uint32_t eta_s = smem_u32(b_base + NSTAGE * 2 * TILE_BYTES + 256);   // [ETA_RING][TILE] fp32, 16-byte aligned
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t g = blockIdx.x % groups, slice = blockIdx.x / groups, slices = gridDim.x / groups;
+    const uint32_t my_tiles = (n_tiles > slice) ? (n_tiles - slice + slices - 1) / slices : 0;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -165,18 +192,24 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     if (warp == 4 * NGRP) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            mbar_expect_tx(a_bar, NWB * NKC * 2 * TILE_BYTES);
+            mbar_expect_tx(a_bar, NWB * NKC * 3 * TILE_BYTES);
             for (int wb = 0; wb < NWB; wb++)
                 for (int kc = 0; kc < NKC; kc++) {
-                    tma_load_2d(a_hi + (wb * NKC + kc) * TILE_BYTES, &map_ah, kc * KD, wb * TILE, a_bar);
-                    tma_load_2d(a_lo + (wb * NKC + kc) * TILE_BYTES, &map_al, kc * KD, wb * TILE, a_bar);
+                    const int wrow = (int)((g * NWB + wb) * TILE);
+                    tma_load_2d(a_hi + (wb * NKC + kc) * TILE_BYTES, &map_ah, kc * KD, wrow, a_bar);
+                    tma_load_2d(a_mi + (wb * NKC + kc) * TILE_BYTES, &map_am, kc * KD, wrow, a_bar);
+                    tma_load_2d(a_lo + (wb * NKC + kc) * TILE_BYTES, &map_al, kc * KD, wrow, a_bar);
                 }
             for (uint32_t it = 0; it < my_tiles; it++) {
-                const int row0 = (int)((blockIdx.x + it * gridDim.x) * TILE);
+                const int row0 = (int)((slice + it * slices) * TILE);
                 for (uint32_t kc = 0; kc < NKC; kc++) {
                     const uint32_t st = it * NKC + kc, s = st % NSTAGE, ph = (st / NSTAGE) & 1u;
                     mbar_wait(&empty_bar[s], ph ^ 1u);
-                    mbar_expect_tx(&full_bar[s], 2 * TILE_BYTES);
+                    mbar_expect_tx(&full_bar[s], 2 * TILE_BYTES + (kc == 0 ? TILE * 4u : 0u));
+                    if (kc == 0)   // the tile's eta0 values (eta0 is padded to a whole tile): one 512-byte bulk copy
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(eta_s + (it % ETA_RING) * TILE * 4u), "l"(eta0 + (size_t)row0), "r"(TILE * 4u),
+                                       "r"(smem_u32(&full_bar[s])) : "memory");
                     tma_load_2d(b_base + (2 * s) * TILE_BYTES, &map_xh, (int)(kc * KD), row0, &full_bar[s]);
                     tma_load_2d(b_base + (2 * s + 1) * TILE_BYTES, &map_xl, (int)(kc * KD), row0, &full_bar[s]);
                 }
@@ -208,13 +241,21 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
 #pragma unroll
                     for (int kc = 0; kc < NKC; kc++) {
                         const uint64_t ah = make_desc(smem_u32(a_hi + (wb * NKC + kc) * TILE_BYTES));
+                        const uint64_t am = make_desc(smem_u32(a_mi + (wb * NKC + kc) * TILE_BYTES));
                         const uint64_t al = make_desc(smem_u32(a_lo + (wb * NKC + kc) * TILE_BYTES));
+                        // smallest products first: they enter the fp32 accumulator before the leading term does
 #pragma unroll
-                        for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, ah + 2 * k, bh[kc] + 2 * k, kc > 0 || k > 0);   // hi*hi
+                        for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, al + 2 * k, bh[kc] + 2 * k, kc > 0 || k > 0);   // lo*hi
+                        if (TERMS >= 5) {
+#pragma unroll
+                            for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, am + 2 * k, bl[kc] + 2 * k, 1);             // mid*lo
+                        }
+#pragma unroll
+                        for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, am + 2 * k, bh[kc] + 2 * k, 1);                 // mid*hi
 #pragma unroll
                         for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, ah + 2 * k, bl[kc] + 2 * k, 1);                 // hi*lo
 #pragma unroll
-                        for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, al + 2 * k, bh[kc] + 2 * k, 1);                 // lo*hi
+                        for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, ah + 2 * k, bh[kc] + 2 * k, 1);                 // hi*hi
                     }
                     tc_commit(&tfull_bar[a]);
                 }
@@ -224,8 +265,8 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         }
     } else {
         // ===================== epilogue groups =====================
-        // Group g drains accumulator stage g, i.e. items g, g+4, g+8, ... (item = tile*NWB + wb), which for
-        // NWB in {1,2,4} all belong to ONE walker block wb = g % NWB: a thread owns exactly one walker.
+        // Group e drains accumulator stage e, i.e. items e, e+4, e+8, ... (item = tile*NWB + wb), which for
+        // NWB in {1,2} all belong to ONE walker block wb = e % NWB: a thread owns exactly one walker.
         // The loops are kept rolled on purpose: fully unrolled, the epilogue was ~100 KB of SASS and the
         // kernel stalled on instruction fetch (ncu: stall_no_inst).
         const uint32_t grp = warp >> 2;
@@ -233,7 +274,7 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         const uint32_t wb_mine = grp % NWB;
         const uint32_t tbase = tmem_base + ((quarter * 32u) << 16) + grp * TILE;
         const uint32_t n_items = my_tiles * NWB;
-        // The walker block arrives pre-scaled by log2(e), so the accumulators hold a = eta*log2(e) and
+        // The dataset planes are pre-scaled by log2(e), so the accumulators hold a = eta*log2(e) and
         //   softplus(eta) = max(eta,0) + ln2*log2(1 + 2^-|a|),   sum_rows max(eta,0) = (sum eta + sum |eta|)/2,
         // where sum_rows eta = (sum_rows x_row) . theta is added analytically by k_glm_finish_tc.  Per element that
         // leaves MUFU.EX2(-|a|), one FFMA on the running product and one FADD on sum|a|.
@@ -242,22 +283,29 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         float hi = 0.f, lo = 0.f;                        // two-float (compensated) sum over this thread's items
         for (uint32_t item = grp; item < n_items; item += NACC) {
             const uint32_t it = item / NWB;
-            const uint32_t row0 = (blockIdx.x + it * gridDim.x) * TILE;
+            const uint32_t row0 = (slice + it * slices) * TILE;
             const uint32_t valid = min((uint32_t)TILE, rows - row0);
             mbar_wait(&tfull_bar[grp], (item / NACC) & 1u);
             tc_fence_after();
             // four independent (product, |a|-sum) chains; the next 16 columns are in flight while 16 are reduced
             float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, p0 = 1.f, p1 = 1.f, p2 = 1.f, p3 = 1.f;
             uint32_t ra[16], rb[16];
-            auto reduce = [&](const uint32_t (&r)[16]) {
+            const uint32_t eta_tile = eta_s + (it % ETA_RING) * TILE * 4u;
+            // a = eta0[row] + (x . delta): the reference part is added here, in round-to-nearest fp32
+            auto reduce = [&](const uint32_t (&r)[16], const uint32_t c) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
+                    float4 eta;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(eta.x), "=f"(eta.y), "=f"(eta.z), "=f"(eta.w) : "r"(eta_tile + (c + j) * 4u));
+                    const float a0 = __uint_as_float(r[j]) + eta.x, a1 = __uint_as_float(r[j + 1]) + eta.y;
+                    const float a2 = __uint_as_float(r[j + 2]) + eta.z, a3 = __uint_as_float(r[j + 3]) + eta.w;
                     if (LINK == 1) {   // sum of 2^a = exp(eta)
-                        m0 += ex2_approx(__uint_as_float(r[j])); m1 += ex2_approx(__uint_as_float(r[j + 1]));
-                        m2 += ex2_approx(__uint_as_float(r[j + 2])); m3 += ex2_approx(__uint_as_float(r[j + 3]));
+                        m0 += ex2_approx(a0); m1 += ex2_approx(a1);
+                        m2 += ex2_approx(a2); m3 += ex2_approx(a3);
                     } else {
-                        const float e0 = fabsf(__uint_as_float(r[j])), e1 = fabsf(__uint_as_float(r[j + 1]));
-                        const float e2 = fabsf(__uint_as_float(r[j + 2])), e3 = fabsf(__uint_as_float(r[j + 3]));
+                        const float e0 = fabsf(a0), e1 = fabsf(a1);
+                        const float e2 = fabsf(a2), e3 = fabsf(a3);
                         const float t0 = ex2_approx(-e0), t1 = ex2_approx(-e1), t2 = ex2_approx(-e2), t3 = ex2_approx(-e3);
                         p0 = fmaf(p0, t0, p0); p1 = fmaf(p1, t1, p1); p2 = fmaf(p2, t2, p2); p3 = fmaf(p3, t3, p3);
                         m0 += e0; m1 += e1; m2 += e2; m3 += e3;
@@ -269,7 +317,7 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
 #pragma unroll 1
             for (uint32_t c = 0; c < TILE; c += 32) {
                 BAY_TMEM_LD16(rb, tbase + c + 16);
-                reduce(ra);
+                reduce(ra, c);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (c + 32 < TILE) {
                     BAY_TMEM_LD16(ra, tbase + c + 32);
@@ -279,7 +327,7 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty_bar[grp]);
                 }
-                reduce(rb);
+                reduce(rb, c + 16);
                 if (c + 32 < TILE) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             }
             // each chain holds 32 factors <= 2.  item value (in units of ln2): sum log2(1+t) + sum|a|/2
@@ -297,7 +345,7 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
             hi = s;
         }
         const double acc64 = ((double)hi + (double)lo) * (LINK == 1 ? 1.0 : 0.6931471805599453);
-        const size_t base = (size_t)(NGRP * blockIdx.x + grp) * ldp + quarter * 32 + lane;
+        const size_t base = (size_t)(NGRP * slice + grp) * ldp + (size_t)g * NWB * TILE + quarter * 32 + lane;
 #pragma unroll
         for (int wb = 0; wb < NWB; wb++) partial[base + wb * TILE] = (wb == (int)wb_mine) ? acc64 : 0.0;
     }
@@ -312,21 +360,30 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
 
 constexpr float LOG2E = 1.4426950408889634f;
 
-// points (SoA, dim x n, pitch) -> bf16 hi/lo planes [n][kdp] (row = walker; kdp = 64 or 128) of theta * log2(e), the
-// A operand
+// points (SoA, dim x n, pitch) -> three bf16 planes [n][kdp] (row = walker; kdp = 64 or 128) of theta - theta0, the
+// A operand: x = hi + mid + lo EXACTLY (8 + 8 + 8 significant bits; both subtractions are exact in fp32)
 __global__ void k_glm_split_points(const float* __restrict__ pts, uint32_t pitch, uint32_t n, uint32_t dim,
-                                   uint32_t kdp, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;    // e = k*kdp + i, coalesced stores
-    if (e >= n * kdp) return;
-    const uint32_t k = e / kdp, i = e % kdp;
-    // dim < kdp: the K extent is zero-padded (the MMA cost is hidden under the MUFU-bound epilogue anyway)
-    const float x = i < dim ? __fmul_rn(pts[(size_t)i * pitch + k], LOG2E) : 0.0f;
+                                   uint32_t kdp, const float* __restrict__ theta0, __nv_bfloat16* __restrict__ hi,
+                                   __nv_bfloat16* __restrict__ mid, __nv_bfloat16* __restrict__ lo) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;    // e = k*kdp + i, coalesced stores
+    if (e >= (uint64_t)n * kdp) return;
+    const uint32_t k = (uint32_t)(e / kdp), i = (uint32_t)(e % kdp);
+    // dim < kdp: the K extent is zero-padded.  The coefficients enter UNSCALED: the factor log2(e) the epilogue wants
+    // lives in the dataset planes (k_glm_split_rows) — rounding theta * log2(e) to fp32 would move every walker by up
+    // to 2^-24 relative, which 10^7 rows amplify to ~0.1 in the log-density (measured), while the same rounding
+    // applied to the dataset is one fixed perturbation shared by all walkers.
+    // delta = theta - theta0: exact whenever the two are within a factor of two of each other, else rounded at
+    // 2^-24 |delta| — far from the reference point, where log-density differences are large
+    const float x = i < dim ? __fsub_rn(pts[(size_t)i * pitch + k], theta0[i]) : 0.0f;
     const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const float r1 = __fsub_rn(x, __bfloat162float(h));
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
     hi[e] = h;
-    lo[e] = __float2bfloat16_rn(x - __bfloat162float(h));
+    mid[e] = m;
+    lo[e] = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(m)));
 }
 
-// sp[k] = sum over the kernel's partial rows + (ln2/2) * sx . (theta_k * log2 e): the analytic sum_rows eta term of
+// sp[k] = sum over the kernel's partial rows + (1/2) * sx . theta_k: the analytic sum_rows eta term of
 // sum max(eta,0) = (sum eta + sum |eta|) / 2.  sx = column sums of the LOCAL rows.  One warp per walker: lanes
 // stride over the partial rows, then a fixed shuffle tree (deterministic: same order on every run and rank).
 __global__ void k_glm_finish_tc(uint32_t n, uint32_t chunks, uint32_t ldp, const double* __restrict__ partial,
@@ -338,13 +395,78 @@ __global__ void k_glm_finish_tc(uint32_t n, uint32_t chunks, uint32_t ldp, const
     for (uint32_t c = lane; c < chunks; c += 32) s += partial[(size_t)c * ldp + k];
     if (link == 0)   // the analytic sum_rows eta / 2 of the softplus split; exp has no such term
         for (uint32_t i = lane; i < dim; i += 32)
-            s += 0.5 * 0.6931471805599453 * sx[i] * (double)__fmul_rn(pts[(size_t)i * pitch + k], LOG2E);
+            s += 0.5 * sx[i] * (double)pts[(size_t)i * pitch + k];
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) sp[k] = s;
 }
 
-// dataset rows [y, x_1..x_dim] (stride dim + 1) -> bf16 hi/lo planes [rows][kdp], zero-padded past dim
+// Reference point, step 1: mean[i] = mean over the n points of coordinate i (double accumulation, one CTA per
+// coordinate).
+__global__ void k_glm_point_mean(const float* __restrict__ pts, uint32_t pitch, uint32_t n, float* __restrict__ mean) {
+    __shared__ double sm[32];
+    const float* row = pts + (size_t)blockIdx.x * pitch;
+    double s = 0.0;
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) s += (double)row[k];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (uint32_t w = 0; w < (blockDim.x + 31) / 32; w++) t += sm[w];
+        mean[blockIdx.x] = (float)(t / (double)n);
+    }
+}
+
+// Reference point, step 2 (one CTA): theta0 = the mean snapped to a coarse grid, q * rint(mean / q) with
+// q = 2^-6 of the largest |mean| rounded down to a power of two.  A PURE function of the call's points (so a chain
+// restored from a checkpoint recomputes the same reference and continues bit for bit), yet stable: once the ensemble
+// has settled the snapped mean changes only when a coordinate crosses a grid line, and only then (*changed = 1) is
+// eta0 recomputed.  |theta - theta0| <= a few grid steps keeps the contracted part ~50x smaller than eta itself.
+__global__ void k_glm_snap_reference(uint32_t dim, const float* __restrict__ mean, float* __restrict__ theta0,
+                                     int* __restrict__ changed, int force) {
+    __shared__ float smax[32];
+    __shared__ int sdiff;
+    float m = 0.0f;
+    for (uint32_t i = threadIdx.x; i < dim; i += blockDim.x) m = fmaxf(m, fabsf(mean[i]));
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = m;
+    if (threadIdx.x == 0) sdiff = force;
+    __syncthreads();
+    m = 0.0f;
+    for (uint32_t w = 0; w < (blockDim.x + 31) / 32; w++) m = fmaxf(m, smax[w]);
+    // power of two not above m, times 2^-6; a non-finite or zero mean falls back to the origin
+    const bool usable = m > 1e-30f && m < 1e30f;
+    const float q = usable ? __uint_as_float((__float_as_uint(m) & 0x7f800000u) - (6u << 23)) : 1.0f;
+    for (uint32_t i = threadIdx.x; i < dim; i += blockDim.x) {
+        const float v = usable ? __fmul_rn(q, rintf(__fdiv_rn(mean[i], q))) : 0.0f;
+        if (v != theta0[i]) { theta0[i] = v; sdiff = 1; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *changed = sdiff;
+}
+
+// eta0[r] = log2(e) * (x_r . theta0), fp64 accumulation, one warp per dataset row [y, x_1..x_dim]; entries past the
+// last row (eta0 is padded to a whole tile) stay zero
+__global__ void k_glm_eta0(const float* __restrict__ data, uint64_t rows, uint32_t dim, const float* __restrict__ theta0,
+                           const int* __restrict__ changed, float* __restrict__ eta0) {
+    if (*changed == 0) return;   // same reference point as the last call: eta0 is current
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < rows; r += warps) {
+        const float* row = data + r * (dim + 1) + 1;
+        double s = 0.0;
+        for (uint32_t i = lane; i < dim; i += 32) s += (double)row[i] * (double)theta0[i];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) eta0[r] = (float)(s * 1.4426950408889634);
+    }
+}
+
+// dataset rows [y, x_1..x_dim] (stride dim + 1) -> bf16 hi/lo planes [rows][kdp] of x * log2(e), zero-padded past dim
+// (the accumulators then hold eta * log2 e, what the exp2-based epilogue consumes)
 __global__ void k_glm_split_rows(const float* __restrict__ data, uint64_t rows, uint32_t dim, uint32_t kdp,
                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
     const uint64_t total = rows * kdp;
@@ -352,7 +474,7 @@ __global__ void k_glm_split_rows(const float* __restrict__ data, uint64_t rows, 
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
         const uint64_t r = e / kdp;
         const uint32_t i = (uint32_t)(e % kdp);
-        const float x = i < dim ? data[r * (dim + 1) + 1 + i] : 0.0f;
+        const float x = i < dim ? __fmul_rn(data[r * (dim + 1) + 1 + i], LOG2E) : 0.0f;
         const __nv_bfloat16 h = __float2bfloat16_rn(x);
         hi[e] = h;
         lo[e] = __float2bfloat16_rn(x - __bfloat162float(h));

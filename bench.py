@@ -441,25 +441,28 @@ def main():
         # dominant kernel: the dataset likelihood (one launch per half-step; propose/finish/accept are ~1 % of it).
         # Dense contraction X(rows x D) . Theta(D x H): 2*rows*D flops per walker-step, bf16-dense peak
         # as the denominator (an fp32-accurate 3-term split can reach at most 1/3 of it).
-        # one launch handles up to 512 walkers against all local rows; a half-step of H = W/2 walkers is ceil(H/512)
-        # back-to-back launches, so the per-launch duration is the half-step time divided by that count
+        # one launch handles up to 1024 walkers (4 groups of 256) against all local rows; a half-step of H = W/2
+        # walkers is ceil(H/1024) back-to-back launches, so the per-launch duration is the half-step time / that count
         kernel_name = "k_glm_loglik_tc"
-        n_groups = -(-(W // 2) // 512)
+        per = 1024
+        n_groups = -(-(W // 2) // per)
         per_launch_ms = per_launch_ms / n_groups
-        flops_per_launch = 2.0 * (wl["rows"] / (world if sharded else 1)) * D * min(W // 2, 512)   # per GPU
+        flops_per_launch = 2.0 * (wl["rows"] / (world if sharded else 1)) * D * min(W // 2, per)   # per GPU
+        terms = 5 if os.environ.get("BAY_GLM_TERMS") == "5" else 4
         peak = float(peaks["bf16_tflops_sustained"]) if peaks else 1400.0
         achieved = flops_per_launch / (per_launch_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 **ncu_traffic(wl["key"], kernel_name), "kernel": kernel_name, "peak_source": peak_src,
                 "flops_per_launch": flops_per_launch,
                 "launch_us": per_launch_ms * 1e3,
-                "executed_mma_tflops": 3.0 * achieved,
-                "note": "achieved counts ALGORITHMIC flops (2*rows*D per walker); fp32-level accuracy from bf16 inputs "
-                        "takes a 3-term split, so the tensor pipe executes 3x that and frac cannot exceed 1/3; "
-                        "see DESIGN.md 4.2 for the pipe utilisations ncu reports",
-                "hbm_view": {"bytes_per_launch": flops_per_launch / min(W // 2, 512) * 2.0,
-                             "achieved_GBps": flops_per_launch / min(W // 2, 512) * 2.0 / (per_launch_ms * 1e-3) / 1e9,
-                             "note": "dataset bytes (bf16 hi+lo planes = 4 B/element) streamed once per launch"}}
+                "executed_mma_tflops": terms * achieved, "mma_terms": terms,
+                "note": "achieved counts ALGORITHMIC flops (2*rows*D per walker).  An accept test on 10^7 rows needs the "
+                        "coefficients represented exactly: theta is split into three bf16 pieces and the dataset into "
+                        f"two, {terms} MMAs per product, so the tensor pipe executes {terms}x the algorithmic flops and frac "
+                        f"cannot exceed 1/{terms}; see DESIGN.md 4.2 for the pipe utilisations ncu reports",
+                "hbm_view": {"bytes_per_launch": flops_per_launch / min(W // 2, per) * 2.0,
+                             "achieved_GBps": flops_per_launch / min(W // 2, per) * 2.0 / (per_launch_ms * 1e-3) / 1e9,
+                             "note": "dataset bytes (bf16 hi+lo planes = 4 B/element) streamed from HBM once per launch"}}
     else:
         kernel_name = sampler_kernel_name(sampler)
         bytes_per_launch = (W / 2) * algorithmic_bytes_per_walker_step(D, p_acc)
@@ -484,7 +487,8 @@ def main():
                              "cost per walker-step is independent of the ensemble size"
                              + (f"; on {wl['cpu_rows']} of {wl['rows']} rows, rate scaled linearly by rows" if wl.get("rows") else "")}
         if wl.get("glm"):   # statically compiled kernel: numbers from the nvcc -Xptxas -v log (profiles/)
-            info = {"block": 576, "grid": "1 CTA per SM (persistent)", "launches_per_half_step": -(-(W // 2) // 512)}
+            info = {"block": 576, "grid": "1 CTA per SM (persistent), 4 walker groups x 37 row-tile slices",
+                    "launches_per_half_step": -(-(W // 2) // 1024)}
         elif sampler.uses_quadform():
             info = {"registers": 128, "block": 512, "grid": "1 CTA per SM (persistent), 128-walker tiles",
                     "shared_bytes": 1024 + 131072 + 8192}
