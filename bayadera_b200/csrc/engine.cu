@@ -278,6 +278,9 @@ struct bay_model {
     CUfunction f_glm_loglik64 = nullptr;   // fp64 yardstick of the likelihood (bay_glm_loglik_probe)
     bool glm = false;
     int glm_link = 0;      // 0 Bernoulli-logit (softplus), 1 Poisson-log (exp)
+    bool rowadd = false;   // generic row-additive model (BAY_MODEL_ROW_ADDITIVE without a GLM flag): rides the GLM host path
+    uint32_t row_stride = 1;                  // its BAY_ROW_STRIDE (read back from the compiled module)
+    CUfunction f_rowadd_loglik = nullptr;
     bool quadform = false; // BAY_MODEL_QUADFORM: logp = -1/2 |U (x - mu)|^2, moves run on k_quadform_move_tc
     bool mirror = false;   // AoS mirror of the ensemble for the partner gather (DIM >= 4, non-GLM)
     bool peers = false;    // kernels store accepted walkers into every rank's ensemble block (multi-GPU mode A)
@@ -343,6 +346,8 @@ struct bay_sampler {
     int64_t params_count = 0;                 // floats in `params` (may be fewer than data_len + params_len)
     // GLM path: repacked dataset, proposals and double-precision log-densities
     uint64_t glm_rows = 0;                    // local rows (this rank's shard)
+    uint64_t glm_rows_total = 0;              // rows of all shards
+    bool own_glm_x = true;                    // glm_x is an allocation of the sampler (generic row-additive: it is `params`)
     float* glm_x = nullptr;                   // rows x D row-major
     double* glm_sy = nullptr;                 // D: X^T y (all-reduced over row shards)
     double* glm_sx = nullptr;                 // D: column sums of the LOCAL rows
@@ -539,11 +544,18 @@ static bool engine_wants_peers(const bay_engine* e) {
     return !(env && env[0] == '0');
 }
 
+// models whose half-step is propose -> dataset likelihood -> accept (glm_program.inc): the two GLM families on
+// tensor cores / SIMT tiles, and any model that states its row decomposition (BAY_MODEL_ROW_ADDITIVE)
+static bool is_rowadd_generic(uint32_t flags) { return (flags & BAY_MODEL_ROW_ADDITIVE) && !(flags & BAY_GLM_ANY); }
+static bool is_dataset_model(int dim, uint32_t flags) {
+    return ((flags & BAY_GLM_ANY) && dim % 4 == 0) || is_rowadd_generic(flags);
+}
+
 // The AoS mirror pays off once a walker spans several 32-byte sectors; GLM models gather only H rows per half-step.
 // BAY_MIRROR=0 in the environment disables it (A/B measurements).
 static bool model_wants_mirror(int dim, uint32_t flags) {
     if (dim < 4) return false;
-    if ((flags & BAY_GLM_ANY) && dim % 4 == 0) return false;
+    if (is_dataset_model(dim, flags)) return false;
     const char* env = getenv("BAY_MIRROR");
     return !(env && env[0] == '0');
 }
@@ -574,7 +586,7 @@ static int nvrtc_build(const char* const* srcs, int nsrc, const char* logfn_name
         src += "\n";
     }
     src += kStretchProgram;
-    if ((flags & BAY_GLM_ANY) && dim % 4 == 0) src += kGlmProgram;
+    if (is_dataset_model(dim, flags)) src += kGlmProgram;
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-default-device", "-lineinfo", "--std=c++17",
                                      "-DREAL=float", "-DREAL2=float2", "-DACCUMULATOR=float",
                                      "-DLOGFN=" + std::string(logfn_name), "-DDIM=" + std::to_string(dim),
@@ -587,6 +599,7 @@ static int nvrtc_build(const char* const* srcs, int nsrc, const char* logfn_name
     if (peers) opts.push_back("-DBAY_PEERS=1");
     if (peers && pull) opts.push_back("-DBAY_PULL=1");
     if (flags & BAY_MODEL_GLM_POISSON) opts.push_back("-DBAY_GLM_LINK=1");
+    if (is_rowadd_generic(flags)) opts.push_back("-DBAY_ROWADD=1");
     if (cparams > 0) opts.push_back("-DBAY_CPARAMS=" + std::to_string(cparams));
     // ensemble traffic policy (stretch_program.inc, BAY_STREAM): large-DIM models keep a per-thread local array and
     // their parameter block in L1, which the once-touched ensemble data would otherwise evict
@@ -656,7 +669,7 @@ extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsr
     USE_ENGINE(e);
     TRY(load_driver());
     std::vector<char> cubin;
-    const bool glm_model = (flags & BAY_GLM_ANY) && dim % 4 == 0;
+    const bool glm_model = is_dataset_model(dim, flags);
     const bool peers = engine_wants_peers(e) && !glm_model;
     const bool pull = peers && engine_wants_pull(e);
     TRY(nvrtc_build(srcs, nsrc, logfn_name, dim, e->wgs, bare_block_for(dim), flags, peers, false, &cubin, nullptr, 0, pull));
@@ -703,17 +716,35 @@ extern "C" int bay_model_compile(bay_engine* e, const char* const* srcs, int nsr
         if (g_cu.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, m->f_accu_loop, e->wgs, 0) == CUDA_SUCCESS)
             m->accu_loop_capacity = per_sm * e->sm_count;
     }
-    if ((flags & BAY_GLM_ANY) && dim % 4 == 0) {
-        struct { const char* name; CUfunction* f; } gfns[] = {
-            {"bay_glm_propose", &m->f_glm_propose}, {"bay_glm_loglik", &m->f_glm_loglik},
-            {"bay_glm_lp_init", &m->f_glm_lp_init}, {"bay_glm_accept", &m->f_glm_accept},
-            {"bay_glm_loglik_f64", &m->f_glm_loglik64}};
+    if (is_dataset_model(dim, flags)) {
+        m->rowadd = is_rowadd_generic(flags);
+        std::vector<std::pair<const char*, CUfunction*>> gfns = {
+            {"bay_glm_propose", &m->f_glm_propose}, {"bay_glm_lp_init", &m->f_glm_lp_init},
+            {"bay_glm_accept", &m->f_glm_accept}};
+        if (m->rowadd) {
+            gfns.push_back({"bay_rowadd_loglik", &m->f_rowadd_loglik});
+        } else {
+            gfns.push_back({"bay_glm_loglik", &m->f_glm_loglik});
+            gfns.push_back({"bay_glm_loglik_f64", &m->f_glm_loglik64});
+        }
         for (auto& fn : gfns) {
-            cr = g_cu.ModuleGetFunction(fn.f, m->mod, fn.name);
+            cr = g_cu.ModuleGetFunction(fn.second, m->mod, fn.first);
             if (cr != CUDA_SUCCESS) {
                 g_cu.ModuleUnload(m->mod);
                 delete m;
-                return cu_fail(cr, fn.name);
+                return cu_fail(cr, fn.first);
+            }
+        }
+        if (m->rowadd) {   // the row stride the model declared (BAY_ROW_STRIDE), exported by the program as a global
+            CUdeviceptr dptr = 0;
+            size_t bytes = 0;
+            cr = g_cu.ModuleGetGlobal(&dptr, &bytes, m->mod, "bay_row_stride");
+            cudaError_t ce = cr == CUDA_SUCCESS ? cudaMemcpy(&m->row_stride, reinterpret_cast<void*>(dptr), sizeof(uint32_t), cudaMemcpyDeviceToHost)
+                                                : cudaErrorUnknown;
+            if (ce != cudaSuccess || m->row_stride < 1) {
+                g_cu.ModuleUnload(m->mod);
+                delete m;
+                return fail(BAY_ECOMPILE, "row-additive model: cannot read BAY_ROW_STRIDE from the compiled program");
             }
         }
         m->glm = true;

@@ -513,6 +513,18 @@ __global__ void k_glm_finish(uint32_t H, uint32_t chunks, const double* __restri
     sp[k] = s;
 }
 
+// generic row-additive path: one warp per walker sums its row-chunk partials — lanes stride over the chunks, then a
+// fixed shuffle tree (deterministic: the same order on every run and every rank)
+__global__ void k_rowadd_finish(uint32_t H, uint32_t chunks, const double* __restrict__ partial, double* __restrict__ sp) {
+    const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (k >= H) return;
+    double s = 0.0;
+    for (uint32_t c = lane; c < chunks; c += 32) s += partial[(size_t)c * H + k];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) sp[k] = s;
+}
+
 // same with an explicit leading dimension of the partial matrix
 __global__ void k_glm_finish_ld(uint32_t n, uint32_t chunks, uint32_t ldp, const double* __restrict__ partial,
                                 double* __restrict__ sp) {

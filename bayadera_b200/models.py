@@ -37,6 +37,9 @@ QUADFORM = 0x10
 _SIG = ("const uint32_t data_len, const uint32_t params_len, const REAL* params, "
         "const uint32_t dim, const REAL* x")
 _LIK_SIG = "const uint32_t data_len, const REAL* data, const uint32_t dim, const REAL* x"
+# row decomposition of a likelihood (engine extension, ignored by the reference): one data row / the row-free rest
+_ROW_SIG = "const REAL* row, const uint32_t dim, const REAL* x"
+_ROWCONST_SIG = "const uint32_t n_rows, const uint32_t dim, const REAL* x"
 
 
 def _fn(name: str, body: str, sig: str = _SIG) -> str:
@@ -74,6 +77,10 @@ GAUSSIAN_SRC = _wrap(
         "        REAL acc = gaussian_kernel(mu, sigma, data[0]) + data_len * gaussian_norm(sigma);\n"
         "        for (uint32_t i = 1; i < data_len; i++) acc += gaussian_kernel(mu, sigma, data[i]);\n"
         "        return acc;", _LIK_SIG),
+    # the same likelihood, stated as a sum over data rows for the engine's row-additive path (glm_program.inc)
+    _fn("gaussian_rowlik", "return gaussian_kernel(x[0], x[1], row[0]);", _ROW_SIG),
+    _fn("gaussian_rowlik_const",
+        "return (0.0f < x[1]) ? n_rows * gaussian_norm(x[1]) : nanf(\"NaN\");", _ROWCONST_SIG),
 )
 
 # --- student-t: params [nu mu sigma logscale]; K/cuda/distributions/student-t.cu ------------
@@ -98,6 +105,10 @@ STUDENT_T_SRC = _wrap(
         "        REAL acc = 0.0;\n"
         "        for (uint32_t i = 0; i < data_len; i++) acc += (student_t_kernel(nu, mu, sigma, data[i]) + norm);\n"
         "        return acc;", _LIK_SIG),
+    _fn("student_t_rowlik", "return student_t_kernel(x[0], x[1], x[2], row[0]);", _ROW_SIG),
+    _fn("student_t_rowlik_const",
+        "return ((0.0f < x[0]) && (0.0f < x[2])) ? n_rows * student_t_norm(x[0], x[2]) : nanf(\"NaN\");",
+        _ROWCONST_SIG),
 )
 
 # --- beta: params [a b -lbeta(a,b)]; K/cuda/distributions/beta.cu ---------------------------
@@ -187,9 +198,10 @@ def _lim(*pairs: Sequence[float]) -> np.ndarray:
 
 UNIFORM = DeviceModel("uniform", (UNIFORM_SRC,), "uniform_logpdf", 1, 2, None, "uniform_logpdf")
 GAUSSIAN = DeviceModel("gaussian", (GAUSSIAN_SRC,), "gaussian_mcmc_logpdf", 1, 2, None, "gaussian_logpdf",
-                       "gaussian_loglik")
+                       "gaussian_loglik", meta={"rowlik": ("gaussian_rowlik", "gaussian_rowlik_const", 1)})
 STUDENT_T = DeviceModel("student_t", (STUDENT_T_SRC,), "student_t_mcmc_logpdf", 1, 4, None,
-                        "student_t_logpdf", "student_t_loglik")
+                        "student_t_logpdf", "student_t_loglik",
+                        meta={"rowlik": ("student_t_rowlik", "student_t_rowlik_const", 1)})
 BETA = DeviceModel("beta", (BETA_SRC,), "beta_mcmc_logpdf", 1, 3, _lim((0.0, 1.0)), "beta_logpdf")
 EXPONENTIAL = DeviceModel("exponential", (EXPONENTIAL_SRC,), "exponential_mcmc_logpdf", 1, 2, None,
                           "exponential_logpdf")
@@ -201,15 +213,25 @@ BINOMIAL = DeviceModel("binomial", (BINOMIAL_SRC,), "binomial_mcmc_logpdf", 1, 2
 DISTRIBUTIONS = {m.name: m for m in (UNIFORM, GAUSSIAN, STUDENT_T, BETA, EXPONENTIAL, ERLANG, GAMMA, BINOMIAL)}
 
 
-def posterior_model(prior: DeviceModel, name: str, likelihood: DeviceModel) -> DeviceModel:
+def posterior_model(prior: DeviceModel, name: str, likelihood: DeviceModel, row_additive: bool = True) -> DeviceModel:
     """``(posterior-model prior name likelihood)``: dimension, params-size and limits come from
     the prior; sources = distinct(prior ∪ likelihood) + the generated pair (models.clj:102-115)."""
     if likelihood.loglik is None or prior.logpdf is None:
         raise ValueError("posterior needs a likelihood with loglik and a prior with logpdf")
     srcs = list(dict.fromkeys(prior.source + likelihood.source))
     srcs.append(posterior_source(name, likelihood.loglik, prior.logpdf))
+    flags = prior.flags
+    rowlik = likelihood.meta.get("rowlik") if row_additive else None
+    if rowlik:
+        # the likelihood states its row decomposition: the engine streams the dataset ONCE per 128 walkers through
+        # shared memory instead of once per walker (the serial loop above stays: it is the oracle and the
+        # density-engine path).  Macros only — the reference's compiler would simply ignore them.
+        fn, const_fn, stride = rowlik
+        srcs.append(f"#define BAY_ROW_STRIDE {stride}\n#define BAY_ROWLIK {fn}\n#define BAY_ROWLIK_CONST {const_fn}\n"
+                    f"#define BAY_PRIOR {prior.logpdf}\n")
+        flags |= ROW_ADDITIVE
     return DeviceModel(name, tuple(srcs), f"{name}_mcmc_logpdf", prior.dimension, prior.params_size,
-                       prior.limits, f"{name}_logpdf", likelihood.loglik, prior.flags)
+                       prior.limits, f"{name}_logpdf", likelihood.loglik, flags)
 
 
 # ------------------------------------------------------------------------------------------
@@ -232,6 +254,38 @@ def binomial_lik_params(n: float, k: float) -> np.ndarray:
 # ==========================================================================================
 # Models for BASELINE.json configs 3-5 (authored here; not in the reference tree)
 # ==========================================================================================
+
+def mean_sd_prior() -> DeviceModel:
+    """A 2-D prior for the parameters (mu, sigma) of ``gaussian_loglik``: mu ~ N(m0, s0), sigma ~ Exponential(lam),
+    independent.  params = [m0 s0 lam]."""
+    src = _wrap(_fn("mean_sd_logpdf",
+                    "const REAL t = (x[0] - params[0]) / params[1];\n"
+                    "        if (!(0.0f < x[1])) return nanf(\"NaN\");\n"
+                    "        return -0.5f * t * t - log(params[1]) - 0.9189385332046727f + log(params[2]) - params[2] * x[1];"))
+    return DeviceModel("mean_sd", (src,), "mean_sd_logpdf", 2, 3, _lim((-10.0, 10.0), (0.1, 10.0)), "mean_sd_logpdf")
+
+
+def gaussian_mean_sd_posterior(row_additive: bool = True) -> DeviceModel:
+    """Posterior of (mu, sigma) given i.i.d. Gaussian data: the reference's ``gaussian_loglik``
+    (K/cuda/distributions/gaussian.cu:36-46) under the posterior template, with the row-additive metadata."""
+    return posterior_model(mean_sd_prior(), "gauss_ms", GAUSSIAN, row_additive=row_additive)
+
+
+def nu_mean_sd_prior() -> DeviceModel:
+    """A 3-D prior for (nu, mu, sigma) of ``student_t_loglik``: nu - 1 ~ Exponential(1/29) (Kruschke), mu ~ N(m0, s0),
+    sigma ~ Exponential(lam).  params = [m0 s0 lam]."""
+    src = _wrap(_fn("nu_mean_sd_logpdf",
+                    "const REAL t = (x[1] - params[0]) / params[1];\n"
+                    "        if (!((1.0f < x[0]) && (0.0f < x[2]))) return nanf(\"NaN\");\n"
+                    "        return -(x[0] - 1.0f) / 29.0f - 0.5f * t * t - log(params[1]) + log(params[2]) - params[2] * x[2];"))
+    return DeviceModel("nu_mean_sd", (src,), "nu_mean_sd_logpdf", 3, 3, _lim((2.0, 40.0), (-10.0, 10.0), (0.1, 10.0)),
+                       "nu_mean_sd_logpdf")
+
+
+def student_t_posterior(row_additive: bool = True) -> DeviceModel:
+    """Robust location/scale posterior: ``student_t_loglik`` (K/cuda/distributions/student-t.cu:40-53)."""
+    return posterior_model(nu_mean_sd_prior(), "robust", STUDENT_T, row_additive=row_additive)
+
 
 def beta_binomial_posterior() -> DeviceModel:
     """config 2: binomial likelihood x beta prior (T/internal/nvidia_gtx_test.clj:135-151,

@@ -55,6 +55,8 @@ def _compile_check(model, wgs=256):
 ALL_MODELS = list(models.DISTRIBUTIONS.values()) + [
     models.beta_binomial_posterior(),
     models.posterior_model(models.GAUSSIAN, "gg", models.GAUSSIAN),
+    models.gaussian_mean_sd_posterior(),          # generic row-additive path (bay_rowadd_loglik)
+    models.student_t_posterior(),
     models.therapeutic_touch_model(),
     models.logistic_regression_model(64),
     models.mvn_model(100),
