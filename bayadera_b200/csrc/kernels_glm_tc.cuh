@@ -420,10 +420,11 @@ __global__ void k_glm_point_mean(const float* __restrict__ pts, uint32_t pitch, 
 }
 
 // Reference point, step 2 (one CTA): theta0 = the mean snapped to a coarse grid, q * rint(mean / q) with
-// q = 2^-6 of the largest |mean| rounded down to a power of two.  A PURE function of the call's points (so a chain
+// q = 2^-4 of the largest |mean| rounded down to a power of two.  A PURE function of the call's points (so a chain
 // restored from a checkpoint recomputes the same reference and continues bit for bit), yet stable: once the ensemble
 // has settled the snapped mean changes only when a coordinate crosses a grid line, and only then (*changed = 1) is
-// eta0 recomputed.  |theta - theta0| <= a few grid steps keeps the contracted part ~50x smaller than eta itself.
+// eta0 recomputed.  |theta - theta0| <= q/2 + the ensemble's spread keeps the contracted part >= 10x smaller than
+// eta itself, which puts the tensor-core accumulation error at the level of an fp32 traversal's summation noise.
 __global__ void k_glm_snap_reference(uint32_t dim, const float* __restrict__ mean, float* __restrict__ theta0,
                                      int* __restrict__ changed, int force) {
     __shared__ float smax[32];
@@ -437,9 +438,9 @@ __global__ void k_glm_snap_reference(uint32_t dim, const float* __restrict__ mea
     __syncthreads();
     m = 0.0f;
     for (uint32_t w = 0; w < (blockDim.x + 31) / 32; w++) m = fmaxf(m, smax[w]);
-    // power of two not above m, times 2^-6; a non-finite or zero mean falls back to the origin
+    // power of two not above m, times 2^-4; a non-finite or zero mean falls back to the origin
     const bool usable = m > 1e-30f && m < 1e30f;
-    const float q = usable ? __uint_as_float((__float_as_uint(m) & 0x7f800000u) - (6u << 23)) : 1.0f;
+    const float q = usable ? __uint_as_float((__float_as_uint(m) & 0x7f800000u) - (4u << 23)) : 1.0f;
     for (uint32_t i = threadIdx.x; i < dim; i += blockDim.x) {
         const float v = usable ? __fmul_rn(q, rintf(__fdiv_rn(mean[i], q))) : 0.0f;
         if (v != theta0[i]) { theta0[i] = v; sdiff = 1; }

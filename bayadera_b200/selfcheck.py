@@ -115,6 +115,7 @@ def glm_delta_logp(sampler, theta_center: np.ndarray, scale: float, pairs: int =
     own, ref = sampler.glm_loglik_probe(pts, 0), sampler.glm_loglik_probe(pts, 2)
     d_own, d_ref = own[pairs:] - own[:pairs], ref[pairs:] - ref[:pairs]
     err = np.abs(d_own - d_ref)
-    return {"ok": bool(err.max() < 1e-2), "pairs": pairs, "max_abs_err": float(err.max()), "mean_abs_err": float(err.mean()),
+    # an fp32 traversal of 10^7 rows carries ~2.5e-3 mean / 1e-2 max of summation noise itself (tests/test_gpu_glm.py)
+    return {"ok": bool(err.mean() < 1e-2 and err.max() < 5e-2), "pairs": pairs, "max_abs_err": float(err.max()), "mean_abs_err": float(err.mean()),
             "mean_abs_dlogp": float(np.abs(d_ref).mean()),
             "level_rel_err": float(np.abs(own - ref).max() / np.abs(ref).max())}

@@ -30,7 +30,18 @@ def gaussian_data(n, mu=2.5, sd=1.7, seed=3):
     return np.concatenate([(mu + sd * rng.standard_normal(n)).astype(np.float32), f32([0.0, 5.0, 0.5])])
 
 
-@pytest.mark.parametrize("n,walkers", [(1, 512), (7, 512), (1000, 1024), (4099, 1536), (50_000, 1024)])
+def gaussian_posterior_fp64(params, xs):
+    """The model in fp64 closed form: the yardstick where the reference's own fp32 `REAL acc` loop (and so the serial
+    oracle) is the less accurate party — 2e4 sequential fp32 additions at |acc| ~ 5e4 wander by ~1e-5 relative."""
+    data, (m0, s0, lam) = params[:-3].astype(np.float64), params[-3:].astype(np.float64)
+    mu, sd = xs[:, 0].astype(np.float64), xs[:, 1].astype(np.float64)
+    ss = ((data[None, :] - mu[:, None]) ** 2).sum(axis=1)
+    lik = -ss / (2.0 * sd * sd) + data.size * (-np.log(sd) - 0.9189385332046727)
+    prior = -0.5 * ((mu - m0) / s0) ** 2 - np.log(s0) - 0.9189385332046727 + np.log(lam) - lam * sd
+    return lik + prior
+
+
+@pytest.mark.parametrize("n,walkers", [(1, 512), (7, 512), (1000, 1024), (4099, 1536)])
 def test_gaussian_posterior_logdensity_and_moves_match_oracle(factory, n, walkers):
     model = models.gaussian_mean_sd_posterior()
     assert model.flags & models.ROW_ADDITIVE
@@ -42,6 +53,21 @@ def test_gaussian_posterior_logdensity_and_moves_match_oracle(factory, n, walker
     assert np.array_equal(st["xs"].reshape(-1), cpu.xs)
     assert logpdf_close(st["logfn"], cpu.lp, rtol=1e-5).all()
     check_steplocked(gpu, cpu, steps=3, a=2.0, tie_tol=5e-3, exact_lp=False)
+
+
+@pytest.mark.parametrize("n", [50_000, 1_000_000])
+def test_gaussian_posterior_large_dataset_against_fp64(factory, n):
+    """10^6 data: the tiled path (fp32 inside a 1024-row tile, double across tiles) against the fp64 closed form at
+    1e-6 relative — ten times inside the north-star tolerance, and closer than the reference-style serial loop."""
+    model = models.gaussian_mean_sd_posterior()
+    params = gaussian_data(n, seed=17)
+    gpu = factory.mcmc_factory(model).create_sampler(5, 1024, params).init_position(6, model.limits_array())
+    xs, lp64 = gpu.get_state64()
+    want = gaussian_posterior_fp64(params, xs)
+    assert np.abs(lp64 / want - 1.0).max() < 1e-6
+    gpu.burn_in(3, 2.0)
+    xs, lp64 = gpu.get_state64()
+    assert np.abs(lp64 / gaussian_posterior_fp64(params, xs) - 1.0).max() < 1e-6
 
 
 def test_row_additive_path_equals_the_serial_kernel(factory):
@@ -56,13 +82,16 @@ def test_row_additive_path_equals_the_serial_kernel(factory):
     b = factory.mcmc_factory(serial).create_sampler(1, walkers, params).init_position(2, lim)
     sa, sb = a.get_state(), b.get_state()
     assert np.array_equal(sa["xs"], sb["xs"])
-    assert logpdf_close(sa["logfn"], sb["logfn"], rtol=1e-5).all()
+    # 2e4 rows: the serial kernel's fp32 accumulator is itself good to ~3e-5 only; both against fp64
+    want = gaussian_posterior_fp64(params, sa["xs"])
+    assert np.abs(sa["logfn"] / want - 1.0).max() < 1e-6
+    assert np.abs(sb["logfn"] / want - 1.0).max() < 1e-4
     a.burn_in(4, 2.0)
     b.burn_in(4, 2.0)
     sa, sb = a.get_state(), b.get_state()
     same = np.all(sa["xs"] == sb["xs"], axis=1)
-    assert same.mean() > 0.99
-    assert logpdf_close(sa["logfn"][same], sb["logfn"][same], rtol=1e-5).all()
+    assert same.mean() > 0.97                        # the serial kernel's summation noise flips near-ties
+    assert np.abs(sa["logfn"] / gaussian_posterior_fp64(params, sa["xs"]) - 1.0).max() < 1e-6
 
 
 def test_student_t_posterior_matches_oracle(factory):
