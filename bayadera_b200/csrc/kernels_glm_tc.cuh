@@ -401,26 +401,29 @@ __global__ void k_glm_finish_tc(uint32_t n, uint32_t chunks, uint32_t ldp, const
     if (lane == 0) sp[k] = s;
 }
 
-// Reference point, step 1: mean[i] = mean over the n points of coordinate i (double accumulation, one CTA per
-// coordinate).
+// Reference point, step 1: mean[i] and rms[i] = sqrt(mean square) over the n points of coordinate i (double
+// accumulation, one CTA per coordinate); mean: dim floats followed by rms: dim floats.
 __global__ void k_glm_point_mean(const float* __restrict__ pts, uint32_t pitch, uint32_t n, float* __restrict__ mean) {
-    __shared__ double sm[32];
+    __shared__ double sm[32], sq[32];
     const float* row = pts + (size_t)blockIdx.x * pitch;
-    double s = 0.0;
-    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) s += (double)row[k];
+    double s = 0.0, s2 = 0.0;
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) { const double v = (double)row[k]; s += v; s2 += v * v; }
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    for (int o = 16; o >= 1; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = s; sq[threadIdx.x >> 5] = s2; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (uint32_t w = 0; w < (blockDim.x + 31) / 32; w++) t += sm[w];
+        double t = 0.0, t2 = 0.0;
+        for (uint32_t w = 0; w < (blockDim.x + 31) / 32; w++) { t += sm[w]; t2 += sq[w]; }
         mean[blockIdx.x] = (float)(t / (double)n);
+        mean[gridDim.x + blockIdx.x] = (float)sqrt(t2 / (double)n);
     }
 }
 
 // Reference point, step 2 (one CTA): theta0 = the mean snapped to a coarse grid, q * rint(mean / q) with
-// q = 2^-4 of the largest |mean| rounded down to a power of two.  A PURE function of the call's points (so a chain
+// q = 2^-3 of the largest coordinate rms (mean AND spread: while the ensemble is still wide the grid is coarse and the
+// reference stays put; once it has contracted the grid follows the size of the coefficients) rounded down to a power
+// of two.  A PURE function of the call's points (so a chain
 // restored from a checkpoint recomputes the same reference and continues bit for bit), yet stable: once the ensemble
 // has settled the snapped mean changes only when a coordinate crosses a grid line, and only then (*changed = 1) is
 // eta0 recomputed.  |theta - theta0| <= q/2 + the ensemble's spread keeps the contracted part >= 10x smaller than
@@ -430,7 +433,7 @@ __global__ void k_glm_snap_reference(uint32_t dim, const float* __restrict__ mea
     __shared__ float smax[32];
     __shared__ int sdiff;
     float m = 0.0f;
-    for (uint32_t i = threadIdx.x; i < dim; i += blockDim.x) m = fmaxf(m, fabsf(mean[i]));
+    for (uint32_t i = threadIdx.x; i < dim; i += blockDim.x) m = fmaxf(m, mean[dim + i]);
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = m;
@@ -438,9 +441,9 @@ __global__ void k_glm_snap_reference(uint32_t dim, const float* __restrict__ mea
     __syncthreads();
     m = 0.0f;
     for (uint32_t w = 0; w < (blockDim.x + 31) / 32; w++) m = fmaxf(m, smax[w]);
-    // power of two not above m, times 2^-4; a non-finite or zero mean falls back to the origin
+    // power of two not above m, times 2^-3; a non-finite or zero mean falls back to the origin
     const bool usable = m > 1e-30f && m < 1e30f;
-    const float q = usable ? __uint_as_float((__float_as_uint(m) & 0x7f800000u) - (4u << 23)) : 1.0f;
+    const float q = usable ? __uint_as_float((__float_as_uint(m) & 0x7f800000u) - (3u << 23)) : 1.0f;
     for (uint32_t i = threadIdx.x; i < dim; i += blockDim.x) {
         const float v = usable ? __fmul_rn(q, rintf(__fdiv_rn(mean[i], q))) : 0.0f;
         if (v != theta0[i]) { theta0[i] = v; sdiff = 1; }
@@ -449,20 +452,34 @@ __global__ void k_glm_snap_reference(uint32_t dim, const float* __restrict__ mea
     if (threadIdx.x == 0) *changed = sdiff;
 }
 
-// eta0[r] = log2(e) * (x_r . theta0), fp64 accumulation, one warp per dataset row [y, x_1..x_dim]; entries past the
-// last row (eta0 is padded to a whole tile) stay zero
+// eta0[r] = log2(e) * (x_r . theta0), fp64 accumulation; a warp takes FOUR dataset rows [y, x_1..x_dim] at a time so
+// that enough loads are in flight to stream the rows at HBM speed; entries past the last row (eta0 is padded to a
+// whole tile) stay zero
 __global__ void k_glm_eta0(const float* __restrict__ data, uint64_t rows, uint32_t dim, const float* __restrict__ theta0,
                            const int* __restrict__ changed, float* __restrict__ eta0) {
     if (*changed == 0) return;   // same reference point as the last call: eta0 is current
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t r = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < rows; r += warps) {
-        const float* row = data + r * (dim + 1) + 1;
-        double s = 0.0;
-        for (uint32_t i = lane; i < dim; i += 32) s += (double)row[i] * (double)theta0[i];
+    const uint64_t stride = dim + 1;
+    for (uint64_t r0 = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4; r0 < rows; r0 += warps * 4) {
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        for (uint32_t i = lane; i < dim; i += 32) {
+            const double t = (double)theta0[i];
+            float x[4];
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) eta0[r] = (float)(s * 1.4426950408889634);
+            for (int q = 0; q < 4; q++) x[q] = (r0 + q < rows) ? __ldcs(data + (r0 + q) * stride + 1 + i) : 0.0f;
+#pragma unroll
+            for (int q = 0; q < 4; q++) s[q] += (double)x[q] * t;
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+        }
+        if (lane < 4 && r0 + lane < rows) {
+            const double v = lane == 0 ? s[0] : (lane == 1 ? s[1] : (lane == 2 ? s[2] : s[3]));
+            eta0[r0 + lane] = (float)(v * 1.4426950408889634);
+        }
     }
 }
 
