@@ -226,6 +226,161 @@ __global__ void k_hist_soa(const float* __restrict__ xs, uint64_t pitch, uint64_
     }
 }
 
+// ---------------------------------------------------------------------------
+// The same three estimate passes over the reference's own layout: element (dimension d, sample w) at
+// data[offset + ld*w + d] (column-major DIM x n, what GTXDatasetEngine receives, estimate.cu:22,109,165, and what
+// the sampler's AoS mirror is).  A sample's coordinates are contiguous, so a warp reads them with lanes along d —
+// 128-byte coalesced — and walks the samples; nothing is transposed first.  J = ceil(dims per CTA / 32) register
+// slots per lane; blockIdx.y selects the chunk of 32*J dimensions.
+// ---------------------------------------------------------------------------
+template <int J>
+__global__ void __launch_bounds__(256) k_minmax_aos(const float* __restrict__ data, uint64_t offset, uint64_t ld,
+                                                    uint32_t dim, uint64_t n, uint32_t* __restrict__ mm) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t d0 = blockIdx.y * 32u * J;
+    float lo[J], hi[J];
+#pragma unroll
+    for (int j = 0; j < J; j++) { lo[j] = INFINITY; hi[j] = -INFINITY; }
+    const uint64_t stride = (uint64_t)gridDim.x * nw;
+    const float* base = data + offset + d0 + lane;
+    for (uint64_t w = (uint64_t)blockIdx.x * nw + warp; w < n; w += 4 * stride) {
+        float v[4][J];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const uint64_t ww = w + r * stride;
+#pragma unroll
+            for (int j = 0; j < J; j++)
+                v[r][j] = (ww < n && d0 + lane + 32u * j < dim) ? __ldcs(base + ld * ww + 32u * j) : NAN;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int j = 0; j < J; j++) { lo[j] = fminf(lo[j], v[r][j]); hi[j] = fmaxf(hi[j], v[r][j]); }   // NaN ignored
+    }
+    __shared__ float slo[8][32 * J], shi[8][32 * J];
+#pragma unroll
+    for (int j = 0; j < J; j++) { slo[warp][lane + 32 * j] = lo[j]; shi[warp][lane + 32 * j] = hi[j]; }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 32u * J; i += blockDim.x) {
+        float a = INFINITY, b = -INFINITY;
+        for (uint32_t q = 0; q < nw; q++) { a = fminf(a, slo[q][i]); b = fmaxf(b, shi[q][i]); }
+        if (d0 + i < dim) { atomicMin(&mm[2 * (d0 + i)], f2ord(a)); atomicMax(&mm[2 * (d0 + i) + 1], f2ord(b)); }
+    }
+}
+
+// shifted sums S1 = sum(x - p), S2 = sum((x - p)^2), pivot p = the dimension's first sample; fp32 over a strip of
+// rows, double across strips / warps / CTAs (same arithmetic as k_moments_soa).  acc: dim x 2 doubles.
+template <int J>
+__global__ void __launch_bounds__(256) k_moments_aos(const float* __restrict__ data, uint64_t offset, uint64_t ld,
+                                                     uint32_t dim, uint64_t n, double* __restrict__ acc) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t d0 = blockIdx.y * 32u * J;
+    const float* base = data + offset + d0 + lane;
+    float p[J];
+    double s1[J], s2[J];
+#pragma unroll
+    for (int j = 0; j < J; j++) {
+        p[j] = (d0 + lane + 32u * j < dim) ? __ldg(base + 32u * j) : 0.0f;
+        s1[j] = 0.0; s2[j] = 0.0;
+    }
+    const uint64_t stride = (uint64_t)gridDim.x * nw;
+    uint64_t w = (uint64_t)blockIdx.x * nw + warp;
+    while (w < n) {
+        float f1[J], f2[J];
+#pragma unroll
+        for (int j = 0; j < J; j++) { f1[j] = 0.f; f2[j] = 0.f; }
+#pragma unroll 2
+        for (int t = 0; t < 8 && w < n; t += 4) {
+            float v[4][J];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const uint64_t ww = w + r * stride;
+#pragma unroll
+                for (int j = 0; j < J; j++)
+                    v[r][j] = (ww < n && d0 + lane + 32u * j < dim) ? __ldcs(base + ld * ww + 32u * j) : p[j];
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int j = 0; j < J; j++) { const float a = v[r][j] - p[j]; f1[j] += a; f2[j] = fmaf(a, a, f2[j]); }
+            w += 4 * stride;
+        }
+#pragma unroll
+        for (int j = 0; j < J; j++) { s1[j] += (double)f1[j]; s2[j] += (double)f2[j]; }
+    }
+    __shared__ double a1[8][32 * J], a2[8][32 * J];
+#pragma unroll
+    for (int j = 0; j < J; j++) { a1[warp][lane + 32 * j] = s1[j]; a2[warp][lane + 32 * j] = s2[j]; }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 32u * J; i += blockDim.x) {
+        double x = 0.0, y = 0.0;
+        for (uint32_t q = 0; q < nw; q++) { x += a1[q][i]; y += a2[q][i]; }
+        if (d0 + i < dim) { atomicAdd(&acc[2 * (d0 + i)], x); atomicAdd(&acc[2 * (d0 + i) + 1], y); }
+    }
+}
+
+// pivots for k_moments_finish when the data is AoS: xs[d*pitch] is replaced by data[offset + d]
+__global__ void k_moments_finish_aos(uint32_t dim, uint64_t n, const float* __restrict__ data, uint64_t offset,
+                                     const double* __restrict__ acc, int mode, float* __restrict__ out) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= dim) return;
+    const double p = (double)data[offset + d];
+    const double m1 = acc[2 * d] / (double)n;
+    double var = acc[2 * d + 1] / (double)n - m1 * m1;
+    var = var < 0.0 ? 0.0 : var;
+    out[d] = mode == 0 ? (float)(p + m1) : (mode == 1 ? (float)var : (float)sqrt(var));
+}
+
+// histogram over AoS data: the CTA keeps bins x (32*J) counters in (dynamic) shared memory — every dimension of its
+// chunk at once — and walks the samples; one global atomic per non-empty bin per CTA at the end.  Same bin arithmetic
+// as k_hist_soa (hist_bin): integer counts, bit-exact against the oracle.
+template <int J>
+__global__ void __launch_bounds__(512) k_hist_aos(const float* __restrict__ data, uint64_t offset, uint64_t ld,
+                                                  uint32_t dim, uint64_t n, const float* __restrict__ limits, uint32_t bins,
+                                                  uint32_t* __restrict__ counts) {
+    // [bins][32*J]: the counter of (bin, local dimension dl) sits in bank dl % 32 = the lane that owns the dimension,
+    // so the 32 shared-memory atomics of a warp instruction never collide, whatever the bins are
+    extern __shared__ uint32_t sh[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t d0 = blockIdx.y * 32u * J;
+    for (uint32_t i = threadIdx.x; i < 32u * J * bins; i += blockDim.x) sh[i] = 0;
+    float lo[J], range[J], scale[J];
+    const float fbins = (float)bins, guard = fbins - 0.5f;
+#pragma unroll
+    for (int j = 0; j < J; j++) {
+        const uint32_t d = d0 + lane + 32u * j;
+        lo[j] = d < dim ? limits[2 * d] : 0.f;
+        range[j] = d < dim ? __fsub_rn(limits[2 * d + 1], lo[j]) : 1.f;
+        scale[j] = __fdividef(fbins, range[j]);
+    }
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * nw;
+    const float* base = data + offset + d0 + lane;
+    for (uint64_t w = (uint64_t)blockIdx.x * nw + warp; w < n; w += 4 * stride) {
+        float v[4][J];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const uint64_t ww = w + r * stride;
+#pragma unroll
+            for (int j = 0; j < J; j++)
+                v[r][j] = (ww < n && d0 + lane + 32u * j < dim) ? __ldcs(base + ld * ww + 32u * j) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            if (w + r * stride >= n) break;
+#pragma unroll
+            for (int j = 0; j < J; j++)
+                if (d0 + lane + 32u * j < dim)
+                    atomicAdd(&sh[hist_bin(v[r][j], lo[j], range[j], fbins, bins, scale[j], guard) * (32u * J) + lane + 32u * j], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 32u * J * bins; i += blockDim.x) {
+        const uint32_t b = i / (32u * J), dl = i - b * (32u * J), c = sh[i];
+        if (c && d0 + dl < dim) atomicAdd(&counts[(size_t)bins * (d0 + dl) + b], c);
+    }
+}
+
 // uint_to_real (estimate.cu:34-44): pdf = (alpha / (hi-lo)) * count
 __global__ void k_uint_to_real(uint32_t bins, uint32_t dim, float alpha,
                                const float* __restrict__ limits,

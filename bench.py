@@ -260,11 +260,45 @@ def run_summary(args):
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / args.steps
         out[name] = {"ms_per_call": ms, "algorithmic_GBps": passes * nbytes / (ms * 1e-3) / 1e9, "passes": passes}
+    # BASELINE configs[4]'s summary workload: histogram! with 256 cycles = 2^28 samples of the 100-D ensemble
+    # (nvidia_gtx.clj:482-512: min/max of the first snapshot, then 255 x (move-bare! + binning) with those limits)
+    s.burn_in(32, 1.25)
+    cycles = 256
+    s.histogram(2)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    s.histogram(cycles)
+    b.record(stream)
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    a.record(stream)
+    s.burn_in(cycles - 1, 1.25)
+    b.record(stream)
+    torch.cuda.synchronize()
+    ms_moves = a.elapsed_time(b)
+    out["histogram! 256 cycles (2^28 samples x 100 dims)"] = {
+        "ms": ms, "ms_per_cycle": ms / cycles, "samples_per_s": cycles * 2 ** 20 / (ms * 1e-3),
+        "of_which_moves_ms": ms_moves,
+        "binning_GBps": (cycles * nbytes) / ((ms - ms_moves) * 1e-3) / 1e9 if ms > ms_moves else None,
+        "note": "binning reads the AoS mirror the tensor-core move maintains; limits from the first snapshot"}
     ds = factory.dataset_engine()
     data = np.random.default_rng(0).random((31 * 2 ** 16, 22), dtype=np.float32)       # T/core_test.clj:19
+    ds.histogram(data[:4096])
     t0 = time.perf_counter()
     ds.histogram(data)
     out["dataset histogram 22 x 2031616 from host (e2e)"] = {"ms_per_call": 1e3 * (time.perf_counter() - t0)}
+    ddev = torch.from_numpy(data).cuda()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    lim = np.zeros((22, 2), dtype=np.float32)
+    from bayadera_b200._lib import check, ptr
+    import ctypes as C
+    for _ in range(5):
+        check(factory._L.bay_dataset_histogram(factory._h, C.c_void_p(ddev.data_ptr()), 1, 22, data.shape[0], 0, 22, ptr(lim),
+                                               None, None, None))
+    dt = (time.perf_counter() - t0) / 5
+    out["dataset histogram 22 x 2031616 on the device"] = {"ms_per_call": 1e3 * dt,
+                                                           "algorithmic_GBps": 2 * data.nbytes / dt / 1e9, "passes": 2}
     print(json.dumps({"workload": "summary engines on the c5 ensemble (100 x 2^20)", "wgs": args.wgs, "results": out}))
 
 
