@@ -489,7 +489,7 @@ def main():
                 **ncu_traffic(wl["key"], kernel_name), "kernel": kernel_name, "peak_source": peak_src,
                 "flops_per_launch": flops_per_launch,
                 "launch_us": per_launch_ms * 1e3,
-                "executed_mma_tflops": terms * achieved, "mma_terms": terms,
+                "executed_mma_tflops": terms * achieved, "mma_terms": terms, "executed_frac": terms * achieved / peak,
                 "note": "achieved counts ALGORITHMIC flops (2*rows*D per walker).  An accept test on 10^7 rows needs the "
                         "coefficients represented exactly: theta is split into three bf16 pieces and the dataset into "
                         f"two, {terms} MMAs per product, so the tensor pipe executes {terms}x the algorithmic flops and frac "
@@ -532,7 +532,9 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
                 "scaling": "strong" if (wl.get("glm") or args.strong) else "weak", "vs_baseline": None,
-                "dtype": "f32 (bf16x3 split on tensor cores, fp32 accumulate)" if wl.get("glm") else "f32",
+                "dtype": "f32 (tensor cores on bf16 pieces: theta in 3, dataset in 2, 4 MMAs per product, fp32 accumulate)"
+                         if wl.get("glm") else ("f32 (tensor cores on fp16 hi/lo pieces, fp32 accumulate)"
+                                                if sampler.uses_quadform() else "f32"),
                 "data": "synthetic",
                 "config": job_config(wl, args),
                 "details": {"walkers_per_gpu": W, "acceptance": round(p_acc, 4),
