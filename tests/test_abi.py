@@ -135,3 +135,28 @@ def test_mix_schedules_expose_their_kind():
     from bayadera_b200 import mcmc
     assert mcmc.pow_n(0.5).pow_n_power == 0.5
     assert mcmc.pow_n(0.5)(9.0)(5) == 2.0 and mcmc.sqrt_n(9.0)(5) == 2.0 and mcmc.minus_n(9.0)(5) == 4.0
+
+
+# ---- the Clojure binding (src/clojure) stays in step with the header ------------------------------
+def test_clojure_binding_declares_only_header_symbols_and_covers_the_protocols():
+    clj = (ROOT / "src" / "clojure" / "uncomplicate" / "bayadera" / "internal" / "device" / "b200.clj").read_text()
+    declared = set(re.findall(r"\(\^\w+ (bay_[a-z0-9_]+) \[", clj))
+    called = set(re.findall(r"\(\.(bay_[a-z0-9_]+) bay", clj))
+    header = set(header_symbols())
+    assert declared and declared <= header, sorted(declared - header)
+    assert called <= declared, sorted(called - declared)
+    # every protocol method of protocols.clj:20-138 that the GTX engines implement has its entry point bound
+    for sym in ("bay_engine_create_current", "bay_model_compile", "bay_sampler_create_dev", "bay_init",
+                "bay_init_position_uniform", "bay_init_position_from", "bay_burn_in", "bay_anneal", "bay_acc_rate",
+                "bay_run_sampler", "bay_init_move", "bay_move", "bay_move_bare", "bay_set_temperature", "bay_sample",
+                "bay_histogram", "bay_mean", "bay_variance", "bay_sd", "bay_info", "bay_dataset_mean",
+                "bay_dataset_variance", "bay_dataset_histogram", "bay_acor", "bay_model_density", "bay_model_evidence",
+                "bay_direct_sample", "bay_sampler_release", "bay_model_release",
+                "bay_engine_release"):
+        assert sym in called, sym
+    for proto in ("MCMC", "MCMCStretch", "RandomSampler", "EstimateEngine", "Location", "Spread", "DatasetEngine",
+                  "AcorEngine", "DensityEngine", "LikelihoodEngine", "RandomSamplerEngine", "SamplerFactory",
+                  "EngineFactory", "ModelProvider", "Releaseable", "Info"):
+        assert re.search(rf"^\s+{proto}\s*$", clj, flags=re.M), proto
+    entry = (ROOT / "src" / "clojure" / "uncomplicate" / "bayadera" / "b200.clj").read_text()
+    assert "with-default-bayadera" in entry and "b200-bayadera-factory" in entry
