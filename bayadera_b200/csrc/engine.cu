@@ -344,6 +344,9 @@ struct bay_sampler {
     float* sample_stage = nullptr;            // staging of sample! results bound for host memory (lazy, grown on demand)
     size_t sample_stage_cap = 0;
     int64_t params_count = 0;                 // floats in `params` (may be fewer than data_len + params_len)
+    uint64_t version = 1;                     // bumped by everything that changes the ensemble
+    uint64_t macc_version = 0;                // ensemble version the moment sums in `macc` were taken from (0: none)
+    bool macc_aos = false;                    // ... and whether they were taken from the AoS mirror
     // GLM path: repacked dataset, proposals and double-precision log-densities
     uint64_t glm_rows = 0;                    // local rows (this rank's shard)
     uint64_t glm_rows_total = 0;              // rows of all shards
@@ -1106,6 +1109,7 @@ extern "C" int bay_init_position_uniform(bay_sampler* s, int32_t seed, const flo
                                                            (uint32_t)s->W);
     CKLAUNCH();
     s->soa_stale = s->soa_own_stale = s->remote_stale = false;   // a full rewrite: every local copy is current
+    s->version++;
     TRY(mirror_sync(s));
     TRY(launch_logfn_all(s));
     TRY(peer_settle(s));
@@ -1125,6 +1129,7 @@ extern "C" int bay_init_position_from(bay_sampler* s, const bay_sampler* other) 
     CK(cudaMemcpyAsync(s->xs, other->xs, sizeof(float) * (size_t)s->D * s->W, cudaMemcpyDeviceToDevice, e->stream));
     TRY(peer_settle(const_cast<bay_sampler*>(other)));
     s->soa_stale = s->soa_own_stale = s->remote_stale = false;
+    s->version++;
     TRY(mirror_sync(s));
     TRY(launch_logfn_all(s));
     TRY(peer_settle(s));
@@ -1284,6 +1289,7 @@ static int quadform_half(bay_sampler* s, int half, uint32_t seed, uint32_t tag, 
 static int half_bare(bay_sampler* s, int half, uint32_t seed, uint32_t tag, float cA, float cB, float cC,
                      float beta, uint32_t step) {
     bay_model* m = s->m;
+    s->version++;
     if (m->glm) return glm_half(s, half, seed, tag, cA, cB, cC, beta, step, 0u);
     if (quadform_usable(s)) return quadform_half(s, half, seed, tag, cA, cB, cC, beta, step);
     TRY(generic_ready(s));
@@ -1314,6 +1320,7 @@ static int half_bare(bay_sampler* s, int half, uint32_t seed, uint32_t tag, floa
 static int half_accu(bay_sampler* s, int half, uint32_t seed, uint32_t tag, float cA, float cB, float cC,
                      uint32_t step) {
     bay_model* m = s->m;
+    s->version++;
     if (m->glm) return glm_half(s, half, seed, tag, cA, cB, cC, 1.0f, step, 1u);
     TRY(generic_ready(s));
     uint32_t K = (uint32_t)s->H, pitch = (uint32_t)s->W, accumulate = half ? 1u : 0u;
@@ -1357,6 +1364,7 @@ static bool loop_usable(const bay_sampler* s, int64_t n) {
 static int move_bare_loop(bay_sampler* s, int64_t n, const float* betas, float cA, float cB, float cC) {
     bay_model* m = s->m;
     bay_engine* e = m->e;
+    s->version++;
     TRY(generic_ready(s));
     float* betas_dev = nullptr;
     if (betas) {
@@ -1537,6 +1545,7 @@ static int move_accu_loop(bay_sampler* s, int64_t n) {
     float cA, cB, cC;
     stretch_coeffs(s->a_move, &cA, &cB, &cC);
     TRY(ensure_means(s, s->means_n + n));
+    s->version++;
     TRY(generic_ready(s));
     TRY(bind_params(s));
     uint32_t K = (uint32_t)s->H, pitch = (uint32_t)s->W, seed = (uint32_t)s->move_seed, step0 = s->move_counter;
