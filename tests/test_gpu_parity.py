@@ -187,6 +187,7 @@ def check_steplocked(gpu, cpu, steps, a, beta_t=1.0, tie_tol=TIE_TOL, exact_lp=T
             else:
                 assert logpdf_close(glp[sl][kept], before_lp[sl][kept]).all()
         cpu.bare_counter += 1
+    print(f"step-locked: {mism_total} near-tie accept mismatches in {steps * 2 * H} walker-steps (band {tie_tol:g})")
     assert mism_total <= max(2, int(2e-4 * steps * 2 * H)), f"too many near-tie mismatches: {mism_total}"
 
 
@@ -214,7 +215,7 @@ def test_mvn_d100(factory):
     st = gpu.get_state()
     assert np.array_equal(st["xs"].reshape(-1), cpu.xs)
     assert logpdf_close(st["logfn"], cpu.lp, rtol=5e-5).all()    # 5050-term fp32 sums, fma vs mul+add
-    check_steplocked(gpu, cpu, steps=2, a=1.2, tie_tol=5e-2)
+    check_steplocked(gpu, cpu, steps=2, a=1.2, tie_tol=2e-3)
 
 
 def test_logistic_regression_small(factory):
@@ -438,12 +439,35 @@ def test_quadform_tensor_core_move_vs_oracle(factory, d, walkers):
     params, _, _ = models.mvn_params(d)
     sf, gpu, cpu = make_pair(factory, model, 3, walkers, params, model.limits_array())
     assert sf.uses_quadform()
-    check_steplocked(gpu, cpu, steps=2, a=1.2, tie_tol=5e-2)
+    # band: the accept ratio uses the approximate __powf / __expf units like the reference's -use_fast_math build;
+    # z^(D-1) = exp2((D-1) lg2 z) carries ~(D-1) * 2^-22 relative
+    check_steplocked(gpu, cpu, steps=2, a=1.2, tie_tol=2e-3)
     # a few unlocked steps, then the log-densities the chain carries must be the model's at the positions it holds
     gpu.burn_in(5, 1.3)
     st = gpu.get_state()
     cpu.set_positions(st["xs"].reshape(-1))
     assert logpdf_close(st["logfn"], cpu.lp, rtol=1e-5).all()
+
+
+def test_quadform_at_config5_size_sampled_against_the_oracle(factory):
+    """BASELINE config 5 at its own size — 2^20 walkers, D = 100 — after tensor-core moves: the log-densities the chain
+    carries, for a random sample of 8192 walkers, against the oracle's serial LOGFN at the positions it holds
+    (north-star tolerance 1e-5 relative), and every position finite."""
+    model = models.mvn_model(100)
+    params, _, _ = models.mvn_params(100)
+    W = 2 ** 20
+    gpu = factory.mcmc_factory(model).create_sampler(31, W, params).init_position(32, model.limits_array())
+    assert gpu.uses_quadform()
+    gpu.burn_in(3, 1.25)
+    st = gpu.get_state()
+    assert np.all(np.isfinite(st["xs"])) and np.all(np.isfinite(st["logfn"]))
+    pick = np.random.default_rng(0).choice(W, 8192, replace=False)
+    cpu = orc.OracleStretch(model, 1, 8192, params, wgs=G.WGS)
+    cpu.set_positions(st["xs"][pick].reshape(-1))
+    assert logpdf_close(st["logfn"][pick], cpu.lp, rtol=1e-5).all()
+    rate = gpu.acc_rate(1.25)
+    assert 0.2 < rate < 0.8, rate
+    gpu.release()
 
 
 def test_quadform_tensor_core_equals_generic_kernel(factory, monkeypatch):
