@@ -118,12 +118,20 @@ __global__ void k_minmax_soa(const float* __restrict__ xs, uint64_t pitch, uint6
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool vec = ((pitch & 3) == 0) && ((((uintptr_t)xs) & 15) == 0);
     if (vec) {
-        const uint64_t n4 = n >> 2;
+        // every CTA streams ONE contiguous segment of the row (sequential 4 KB blocks: DRAM pages stay open)
+        const uint64_t n4 = n >> 2, seg = (n4 + gridDim.x - 1) / gridDim.x;
+        const uint64_t q0 = (uint64_t)blockIdx.x * seg, q1 = q0 + seg < n4 ? q0 + seg : n4;
         const float4* row4 = reinterpret_cast<const float4*>(row);
-        for (uint64_t q = i; q < n4; q += stride) {
-            const float4 v = __ldg(row4 + q);
-            lo = fminf(fminf(lo, v.x), fminf(fminf(v.y, v.z), v.w));
-            hi = fmaxf(fmaxf(hi, v.x), fmaxf(fmaxf(v.y, v.z), v.w));
+        for (uint64_t q = q0 + threadIdx.x; q < q1; q += 4 * blockDim.x) {
+            float4 v[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                v[r] = (q + r * blockDim.x < q1) ? __ldcs(row4 + q + r * blockDim.x) : make_float4(NAN, NAN, NAN, NAN);
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                lo = fminf(fminf(lo, v[r].x), fminf(fminf(v[r].y, v[r].z), v[r].w));
+                hi = fmaxf(fmaxf(hi, v[r].x), fmaxf(fmaxf(v[r].y, v[r].z), v[r].w));
+            }
         }
         for (uint64_t q = (n4 << 2) + i; q < n; q += stride) { lo = fminf(lo, row[q]); hi = fmaxf(hi, row[q]); }
     } else {
@@ -203,14 +211,24 @@ __global__ void k_hist_soa(const float* __restrict__ xs, uint64_t pitch, uint64_
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool vec = ((pitch & 3) == 0) && ((((uintptr_t)xs) & 15) == 0);
     if (vec) {
-        const uint64_t n4 = n >> 2;
+        // every CTA streams ONE contiguous segment of the row (sequential 4 KB blocks: DRAM pages stay open)
+        const uint64_t n4 = n >> 2, seg = (n4 + gridDim.x - 1) / gridDim.x;
+        const uint64_t q0 = (uint64_t)blockIdx.x * seg, q1 = q0 + seg < n4 ? q0 + seg : n4;
         const float4* row4 = reinterpret_cast<const float4*>(row);
-        for (uint64_t q = i; q < n4; q += stride) {
-            const float4 v = __ldg(row4 + q);
+        for (uint64_t q = q0 + threadIdx.x; q < q1; q += 2 * blockDim.x) {
+            const bool two = q + blockDim.x < q1;
+            const float4 v = __ldcs(row4 + q);
+            const float4 w = two ? __ldcs(row4 + q + blockDim.x) : v;
             atomicAdd(&mine[hist_bin(v.x, lo, range, fbins, bins, scale, guard)], 1u);
             atomicAdd(&mine[hist_bin(v.y, lo, range, fbins, bins, scale, guard)], 1u);
             atomicAdd(&mine[hist_bin(v.z, lo, range, fbins, bins, scale, guard)], 1u);
             atomicAdd(&mine[hist_bin(v.w, lo, range, fbins, bins, scale, guard)], 1u);
+            if (two) {
+                atomicAdd(&mine[hist_bin(w.x, lo, range, fbins, bins, scale, guard)], 1u);
+                atomicAdd(&mine[hist_bin(w.y, lo, range, fbins, bins, scale, guard)], 1u);
+                atomicAdd(&mine[hist_bin(w.z, lo, range, fbins, bins, scale, guard)], 1u);
+                atomicAdd(&mine[hist_bin(w.w, lo, range, fbins, bins, scale, guard)], 1u);
+            }
         }
         for (uint64_t q = (n4 << 2) + i; q < n; q += stride)
             atomicAdd(&mine[hist_bin(row[q], lo, range, fbins, bins, scale, guard)], 1u);
@@ -462,15 +480,19 @@ __global__ void k_moments_soa(const float* __restrict__ xs, uint64_t pitch, uint
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool vec = ((pitch & 3) == 0) && ((((uintptr_t)xs) & 15) == 0);
     if (vec) {
-        const uint64_t n4 = n >> 2;
+        // every CTA streams ONE contiguous segment of the row (sequential 4 KB blocks: DRAM pages stay open)
+        const uint64_t n4 = n >> 2, seg = (n4 + gridDim.x - 1) / gridDim.x;
+        const uint64_t q0 = (uint64_t)blockIdx.x * seg, q1 = q0 + seg < n4 ? q0 + seg : n4;
         const float4* row4 = reinterpret_cast<const float4*>(row);
-        uint64_t q = i;
-        while (q < n4) {
+        const float4 pad = make_float4(p, p, p, p);
+        for (uint64_t q = q0 + threadIdx.x; q < q1; q += 8 * blockDim.x) {
+            float4 v[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) v[r] = (q + r * blockDim.x < q1) ? __ldcs(row4 + q + r * blockDim.x) : pad;
             float f1 = 0.f, f2 = 0.f;
-#pragma unroll 4
-            for (int r = 0; r < 8 && q < n4; r++, q += stride) {
-                const float4 v = __ldg(row4 + q);
-                const float a = v.x - p, b = v.y - p, c = v.z - p, e = v.w - p;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const float a = v[r].x - p, b = v[r].y - p, c = v[r].z - p, e = v[r].w - p;
                 f1 += (a + b) + (c + e);
                 f2 += (a * a + b * b) + (c * c + e * e);
             }

@@ -257,8 +257,13 @@ def run_summary(args):
     s = factory.mcmc_factory(m).create_sampler(1, 2 ** 20, models.mvn_params(100)[0]).init_position(2, m.limits_array())
     nbytes = 4.0 * 100 * 2 ** 20
     out = {}
-    for name, fn, passes in (("histogram (min/max + bin)", lambda: s.histogram(1), 2), ("mean", s.mean, 1),
-                             ("variance", s.variance, 1)):
+    def fresh_mean():
+        s.move_bare_half(0)          # a new ensemble state: the moment sums are cached per state
+        return s.mean()
+
+    for name, fn, passes in (("AoS mirror: histogram (min/max + bin)", lambda: s.histogram(1), 2),
+                             ("mean (incl. one half-ensemble move per call)", fresh_mean, 1),
+                             ("variance after mean (same state: no pass)", s.variance, 0)):
         for _ in range(3):
             fn()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -269,6 +274,22 @@ def run_summary(args):
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / args.steps
         out[name] = {"ms_per_call": ms, "algorithmic_GBps": passes * nbytes / (ms * 1e-3) / 1e9, "passes": passes}
+    # the same ensemble held by a sampler that keeps its SoA matrix current (generic kernels): the SoA passes
+    os.environ["BAY_QUADFORM_TC"] = "0"
+    g = factory.mcmc_factory(m).create_sampler(1, 2 ** 20, models.mvn_params(100)[0]).init_position(2, m.limits_array())
+    del os.environ["BAY_QUADFORM_TC"]
+    for name, fn, passes in (("SoA kernels: histogram (min/max + bin)", lambda: g.histogram(1), 2),):
+        for _ in range(3):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(args.steps):
+            fn()
+        b.record(stream)
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / args.steps
+        out[name] = {"ms_per_call": ms, "algorithmic_GBps": passes * nbytes / (ms * 1e-3) / 1e9, "passes": passes}
+    g.release()
     # BASELINE configs[4]'s summary workload: histogram! with 256 cycles = 2^28 samples of the 100-D ensemble
     # (nvidia_gtx.clj:482-512: min/max of the first snapshot, then 255 x (move-bare! + binning) with those limits)
     s.burn_in(32, 1.25)
