@@ -96,6 +96,8 @@ SIGNATURES = {
     "bay_model_logfn": (C.c_int, [_vp, _vp, _i64, _f32, _i64, _f32]),
     "bay_model_density": (C.c_int, [_vp, _vp, _i64, _f32, _i64, C.c_int, _f32]),
     "bay_model_evidence": (C.c_int, [_vp, _vp, _i64, _f32, _i64, C.POINTER(C.c_double)]),
+    "bay_model_density_dev": (C.c_int, [_vp, C.c_uint64, _i64, C.c_uint64, _i64, C.c_int, C.c_uint64]),
+    "bay_model_evidence_dev": (C.c_int, [_vp, C.c_uint64, _i64, C.c_uint64, _i64, C.POINTER(C.c_double)]),
     "bay_direct_sample": (C.c_int, [_vp, C.c_int, _i32, _f32, C.c_int, _i64, _vp, C.c_int]),
     "bay_hdi": (C.c_int, [_vp, C.c_double, _vp, _vp, _vp, C.c_int]),
     "bay_hdi_histogram": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp, _vp, C.c_int]),

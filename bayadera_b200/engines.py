@@ -53,6 +53,12 @@ class B200DistributionEngine:
     def density(self, params, x) -> np.ndarray:
         return self._density(params, x, 1)
 
+    def density_dev(self, params_ptr: int, params_count: int, x_ptr: int, n: int, out_ptr: int,
+                    exponentiate: bool = False) -> None:
+        """The reference's calling convention: params, the DIM x n point matrix and the result are blocks of the
+        engine's CUDA context (nvidia_gtx.clj:83-104); nothing crosses to the host."""
+        check(self._L.bay_model_density_dev(self._sf._h, params_ptr, params_count, x_ptr, n, int(exponentiate), out_ptr))
+
     def release(self) -> None:
         self._sf.release()
 
@@ -68,6 +74,11 @@ class B200LikelihoodEngine(B200DistributionEngine):
         p = _f32(data).reshape(-1)
         out = C.c_double()
         check(self._L.bay_model_evidence(self._sf._h, ptr(p), p.size, pts.reshape(-1), pts.shape[0], C.byref(out)))
+        return out.value
+
+    def evidence_dev(self, data_ptr: int, data_count: int, x_ptr: int, n: int) -> float:
+        out = C.c_double()
+        check(self._L.bay_model_evidence_dev(self._sf._h, data_ptr, data_count, x_ptr, n, C.byref(out)))
         return out.value
 
 

@@ -101,6 +101,40 @@ def mode_b_replicas(multi, single, rank: int, world: int, rows: int = 60_000, d:
             "replicas_identical": bool(replicas), "rows": rows}
 
 
+def mode_b_rowadd(multi, single, rank: int, world: int, n: int = 400_000, walkers: int = 1024) -> dict:
+    """Generic row-additive posterior (gaussian_loglik x a 2-D prior) with its data rows sharded over the ranks against
+    the unsharded sampler: the row-free part of the likelihood must use the GLOBAL row count.  Collective."""
+    from .distributed import shard_rows
+    rng = np.random.default_rng(7)
+    data = (2.5 + 1.7 * rng.standard_normal(n)).astype(np.float32)
+    hyper = f32([0.0, 5.0, 0.5])
+    model = models.gaussian_mean_sd_posterior()
+    b0, b1 = shard_rows(n, world, rank)
+    b0, b1 = (b0 // 4) * 4, (b1 // 4) * 4 if rank < world - 1 else n      # shard starts stay 16-byte aligned
+    sharded = multi.mcmc_factory(model).create_sampler(5, walkers, np.concatenate([data[b0:b1], hyper]))
+    whole = single.mcmc_factory(model).create_sampler(5, walkers, np.concatenate([data, hyper]))
+    for s in (sharded, whole):
+        s.init_position(6, model.limits_array())
+    xs_s, lp_s = sharded.get_state64()
+    xs_w, lp_w = whole.get_state64()
+    rel = float(np.abs(lp_s / lp_w - 1.0).max())
+    ok = bool(np.array_equal(xs_s, xs_w)) and rel < 1e-6
+    for s in (sharded, whole):
+        s.burn_in(4, 2.0)
+    xs_s, lp_s = sharded.get_state64()
+    xs_w, _ = whole.get_state64()
+    agree = float(np.all(xs_s == xs_w, axis=1).mean())
+    ok &= agree > 0.99
+    replicas = True
+    if world > 1:
+        replicas = _all_equal_across_ranks(xs_s) and _all_equal_across_ranks(lp_s)
+    ok &= replicas
+    sharded.release()
+    whole.release()
+    return {"ok": bool(ok), "logdensity_rel_vs_unsharded": rel, "chain_agreement": agree,
+            "replicas_identical": bool(replicas), "data": n}
+
+
 def glm_delta_logp(sampler, theta_center: np.ndarray, scale: float, pairs: int = 256, a: float = 1.2, seed: int = 99) -> dict:
     """Δ(sum of the log-partition) of stretch proposals between walkers scattered at `scale` around `theta_center`,
     by the sampler's own path (tensor cores when eligible) against the fp64 traversal (bay_glm_loglik_probe)."""

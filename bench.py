@@ -480,6 +480,7 @@ def main():
             single = bb.B200BayaderaFactory(device=local_rank, stream=stream.cuda_stream, wgs=args.wgs)
             parity["mode_a_partition_vs_1gpu"] = selfcheck.mode_a_bit_identity(factory, single, world)
             parity["mode_b_row_shards_vs_1gpu"] = selfcheck.mode_b_replicas(factory, single, rank, world)
+            parity["mode_b_rowadd_shards_vs_1gpu"] = selfcheck.mode_b_rowadd(factory, single, rank, world)
         parity["ok"] = all(v.get("ok", False) for v in parity.values())
         ok_t = torch.tensor([1 if parity["ok"] else 0], dtype=torch.int32, device="cuda")
         if world > 1:

@@ -211,6 +211,12 @@ int bay_model_density(bay_model *m, const float *params_host, int64_t params_cou
 /* LikelihoodEngine.evidence (P/:79-80; G/:132-141): mean over the n points of exp(logfn), double accumulation */
 int bay_model_evidence(bay_model *m, const float *params_host, int64_t params_count, const float *x_host,
                        int64_t n, double *out);
+/* the same with every block already in the engine's CUDA context (the reference's callers pass cuda-float blocks,
+ * G/:83-104, 118-141): params_dev params_count floats, x_dev DIM x n column-major, out_dev n floats */
+int bay_model_density_dev(bay_model *m, uint64_t params_dev, int64_t params_count, uint64_t x_dev, int64_t n,
+                          int exponentiate, uint64_t out_dev);
+int bay_model_evidence_dev(bay_model *m, uint64_t params_dev, int64_t params_count, uint64_t x_dev, int64_t n,
+                           double *out);
 /* RandomSamplerEngine.sample [seed params res] (P/:90-92; G/:48-63; K/rng/<family>-sampler.cu): family 0 uniform [a b],
  * 1 gaussian [mu sigma], 2 exponential [lambda], 3 erlang [lambda k]; n a multiple of 4; out: 1 x n. */
 int bay_direct_sample(bay_engine *e, int family, int32_t seed, const float *params_host, int nparams, int64_t n,

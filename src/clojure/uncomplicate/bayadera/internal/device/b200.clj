@@ -96,6 +96,10 @@
                            ^floats out])
   (^int bay_model_evidence [^com.sun.jna.Pointer m ^floats params ^long nparams ^floats x ^long n
                             ^com.sun.jna.ptr.DoubleByReference out])
+  (^int bay_model_density_dev [^com.sun.jna.Pointer m ^long params-dev ^long nparams ^long x-dev ^long n
+                               ^int exponentiate ^long out-dev])
+  (^int bay_model_evidence_dev [^com.sun.jna.Pointer m ^long params-dev ^long nparams ^long x-dev ^long n
+                                ^com.sun.jna.ptr.DoubleByReference out])
   (^int bay_direct_sample [^com.sun.jna.Pointer e ^int family ^int seed ^floats params ^int nparams ^long n
                            ^com.sun.jna.Pointer out ^int out-is-device]))
 
@@ -127,8 +131,13 @@
   ^long [cu-buf]
   (long (uncomplicate.clojurecuda.internal.protocols/ptr cu-buf)))
 
+(defn ^:private dev-addr
+  "CUdeviceptr of the first entry of a cuda-float vector / dense matrix (buffer + offset)."
+  ^long [x]
+  (+ (device-pointer (buffer x)) (* Float/BYTES (long (offset x)))))
+
 (defn ^:private dev-ptr ^Pointer [x]
-  (Pointer. (+ (device-pointer (buffer x)) (* Float/BYTES (long (offset x))))))
+  (Pointer. (dev-addr x)))
 
 (defn ^:private host-floats
   "Column-major float[] copy of a (host or device) Neanderthal vector / matrix."
@@ -177,20 +186,22 @@
   ModelProvider
   (model [_] dist-model)
   DensityEngine
+  ;; params, the DIM x n point matrix (stride = DIM, as the reference's kernels assume, G/:83-104) and the result are
+  ;; cuda-float blocks of ctx: they are handed across as device addresses, nothing is staged through the host
   (log-density [this cu-params x]
     (in-context
      ctx
-     (let [p (host-floats cu-params) xs (host-floats x) n (ncols x) out (float-array n)]
-       (ok! (.bay_model_density bay modl p (alength p) xs (long n) 0 out))
-       (let-release [res (vctr cu-params n)]
-         (transfer! out res)))))
+     (let-release [res (vctr cu-params (ncols x))]
+       (ok! (.bay_model_density_dev bay modl (dev-addr cu-params) (long (dim cu-params)) (dev-addr x)
+                                    (long (ncols x)) 0 (dev-addr res)))
+       res)))
   (density [this cu-params x]
     (in-context
      ctx
-     (let [p (host-floats cu-params) xs (host-floats x) n (ncols x) out (float-array n)]
-       (ok! (.bay_model_density bay modl p (alength p) xs (long n) 1 out))
-       (let-release [res (vctr cu-params n)]
-         (transfer! out res))))))
+     (let-release [res (vctr cu-params (ncols x))]
+       (ok! (.bay_model_density_dev bay modl (dev-addr cu-params) (long (dim cu-params)) (dev-addr x)
+                                    (long (ncols x)) 1 (dev-addr res)))
+       res))))
 
 ;; ============================ Likelihood engine (G/:106-141) =================
 ;; The model handle is compiled with a LOGFN that ignores the hyper-parameters and calls the model's loglik on
@@ -210,23 +221,24 @@
   (log-density [this cu-data x]
     (in-context
      ctx
-     (let [d (host-floats cu-data) xs (host-floats x) n (ncols x) out (float-array n)]
-       (ok! (.bay_model_density bay modl d (alength d) xs (long n) 0 out))
-       (let-release [res (vctr cu-data n)]
-         (transfer! out res)))))
+     (let-release [res (vctr cu-data (ncols x))]
+       (ok! (.bay_model_density_dev bay modl (dev-addr cu-data) (long (dim cu-data)) (dev-addr x)
+                                    (long (ncols x)) 0 (dev-addr res)))
+       res)))
   (density [this cu-data x]
     (in-context
      ctx
-     (let [d (host-floats cu-data) xs (host-floats x) n (ncols x) out (float-array n)]
-       (ok! (.bay_model_density bay modl d (alength d) xs (long n) 1 out))
-       (let-release [res (vctr cu-data n)]
-         (transfer! out res)))))
+     (let-release [res (vctr cu-data (ncols x))]
+       (ok! (.bay_model_density_dev bay modl (dev-addr cu-data) (long (dim cu-data)) (dev-addr x)
+                                    (long (ncols x)) 1 (dev-addr res)))
+       res)))
   LikelihoodEngine
   (evidence [this cu-data x]
     (in-context
      ctx
-     (let [d (host-floats cu-data) xs (host-floats x) out (DoubleByReference.)]
-       (ok! (.bay_model_evidence bay modl d (alength d) xs (long (ncols x)) out))
+     (let [out (DoubleByReference.)]
+       (ok! (.bay_model_evidence_dev bay modl (dev-addr cu-data) (long (dim cu-data)) (dev-addr x)
+                                     (long (ncols x)) out))
        (.getValue out)))))
 
 ;; ============================ Dataset engine (G/:145-228) ====================

@@ -120,6 +120,8 @@ def main():
     assert ra["ok"], ra
     rb = selfcheck.mode_b_replicas(multi, single, rank, world)
     assert rb["ok"], rb
+    rc = selfcheck.mode_b_rowadd(multi, single, rank, world)
+    assert rc["ok"], rc
 
     dist.barrier()
     if rank == 0:

@@ -150,7 +150,7 @@ def test_clojure_binding_declares_only_header_symbols_and_covers_the_protocols()
                 "bay_init_position_uniform", "bay_init_position_from", "bay_burn_in", "bay_anneal", "bay_acc_rate",
                 "bay_run_sampler", "bay_init_move", "bay_move", "bay_move_bare", "bay_set_temperature", "bay_sample",
                 "bay_histogram", "bay_mean", "bay_variance", "bay_sd", "bay_info", "bay_dataset_mean",
-                "bay_dataset_variance", "bay_dataset_histogram", "bay_acor", "bay_model_density", "bay_model_evidence",
+                "bay_dataset_variance", "bay_dataset_histogram", "bay_acor", "bay_model_density_dev", "bay_model_evidence_dev",
                 "bay_direct_sample", "bay_sampler_release", "bay_model_release",
                 "bay_engine_release"):
         assert sym in called, sym

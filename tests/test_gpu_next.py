@@ -144,3 +144,30 @@ def test_mix_in_one_call_equals_protocol_loop(factory, schedule):
     assert ra == rb, (ra, rb)
     assert ra["a"] > 2.0 and 0.2 <= ra["acc-rate"] < ra["acc-rate-2.0"], ra
     assert np.array_equal(sa["xs"], sb["xs"]) and np.array_equal(sa["logfn"], sb["logfn"])
+
+
+def test_density_and_evidence_engines_on_device_blocks():
+    """The reference hands cuda-float blocks to log-density / density / evidence (nvidia_gtx.clj:83-141): the _dev entry
+    points must give what the host-array ones give."""
+    import torch
+    from bayadera_b200.engines import B200DistributionEngine, B200LikelihoodEngine
+    with bb.B200BayaderaFactory(device=0, wgs=256) as factory:
+        dist = B200DistributionEngine(factory, models.GAUSSIAN)
+        params = np.asarray([1.5, 0.7], dtype=np.float32)
+        x = np.linspace(-3, 5, 4001, dtype=np.float32)
+        want_log, want_pdf = dist.log_density(params, x), dist.density(params, x)
+        p_d, x_d = torch.from_numpy(params).cuda(), torch.from_numpy(x).cuda()
+        out = torch.empty(x.size, dtype=torch.float32, device="cuda")
+        dist.density_dev(p_d.data_ptr(), p_d.numel(), x_d.data_ptr(), x.size, out.data_ptr())
+        factory.synchronize()
+        assert np.array_equal(out.cpu().numpy(), want_log)
+        dist.density_dev(p_d.data_ptr(), p_d.numel(), x_d.data_ptr(), x.size, out.data_ptr(), exponentiate=True)
+        factory.synchronize()
+        assert np.array_equal(out.cpu().numpy(), want_pdf)
+        lik = B200LikelihoodEngine(factory, models.BINOMIAL)
+        data = models.binomial_lik_params(50, 15)
+        pts = np.random.default_rng(0).beta(3, 2, 8192).astype(np.float32)
+        d_d, t_d = torch.from_numpy(data).cuda(), torch.from_numpy(pts).cuda()
+        assert lik.evidence_dev(d_d.data_ptr(), d_d.numel(), t_d.data_ptr(), pts.size) == lik.evidence(data, pts)
+        dist.release()
+        lik.release()
