@@ -383,16 +383,31 @@ __global__ void k_glm_split_points(const float* __restrict__ pts, uint32_t pitch
     lo[e] = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(m)));
 }
 
+// The likelihood launches of one call (up to 1024 walkers each) leave their partial sums in consecutive regions of
+// `partial`; ONE finish launch reduces them all.
+struct FinishPlan {
+    uint32_t n_launch;
+    uint32_t k0[8], cnt[8], chunks[8], ldp[8];   // first walker, walkers, partial rows, leading dimension per launch
+    unsigned long long off[8];                   // offset of the launch's region in `partial` (doubles)
+};
+
 // sp[k] = sum over the kernel's partial rows + (1/2) * sx . theta_k: the analytic sum_rows eta term of
 // sum max(eta,0) = (sum eta + sum |eta|) / 2.  sx = column sums of the LOCAL rows.  One warp per walker: lanes
 // stride over the partial rows, then a fixed shuffle tree (deterministic: same order on every run and rank).
-__global__ void k_glm_finish_tc(uint32_t n, uint32_t chunks, uint32_t ldp, const double* __restrict__ partial,
-                                const double* __restrict__ sx, const float* __restrict__ pts, uint32_t pitch,
-                                uint32_t dim, uint32_t link, double* __restrict__ sp) {
-    const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (k >= n) return;
+__global__ void k_glm_finish_tc(const __grid_constant__ FinishPlan plan, uint32_t kbase, uint32_t n,
+                                const double* __restrict__ partial, const double* __restrict__ sx,
+                                const float* __restrict__ pts, uint32_t pitch, uint32_t dim, uint32_t link,
+                                double* __restrict__ sp) {
+    // walkers kbase .. kbase + n - 1 (those the plan's launches cover)
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const uint32_t k = kbase + w;
+    uint32_t l = 0;
+    while (l + 1 < plan.n_launch && k >= plan.k0[l + 1]) l++;
+    const double* part = partial + plan.off[l];
+    const uint32_t kk = k - plan.k0[l], chunks = plan.chunks[l], ldp = plan.ldp[l];
     double s = 0.0;
-    for (uint32_t c = lane; c < chunks; c += 32) s += partial[(size_t)c * ldp + k];
+    for (uint32_t c = lane; c < chunks; c += 32) s += part[(size_t)c * ldp + kk];
     if (link == 0)   // the analytic sum_rows eta / 2 of the softplus split; exp has no such term
         for (uint32_t i = lane; i < dim; i += 32)
             s += 0.5 * sx[i] * (double)pts[(size_t)i * pitch + k];
@@ -401,10 +416,22 @@ __global__ void k_glm_finish_tc(uint32_t n, uint32_t chunks, uint32_t ldp, const
     if (lane == 0) sp[k] = s;
 }
 
-// Reference point, step 1: mean[i] and rms[i] = sqrt(mean square) over the n points of coordinate i (double
-// accumulation, one CTA per coordinate); mean: dim floats followed by rms: dim floats.
-__global__ void k_glm_point_mean(const float* __restrict__ pts, uint32_t pitch, uint32_t n, float* __restrict__ mean) {
+// Reference point of the contraction, ONE launch (grid = dim CTAs).
+// Step 1, every CTA: mean and rms = sqrt(mean square) of its coordinate over the n points (double accumulation).
+// Step 2, the CTA that finishes last: theta0 = the mean snapped to a coarse grid, q * rint(mean / q) with q = 2^-3 of
+// the largest coordinate rms (mean AND spread: while the ensemble is still wide the grid is coarse and the reference
+// stays put; once it has contracted the grid follows the size of the coefficients) rounded down to a power of two.
+// A PURE function of the points (so a chain restored from a checkpoint recomputes the same reference and continues
+// bit for bit), yet stable: once the ensemble has settled the snapped mean changes only when a coordinate crosses a
+// grid line, and only then (flags[0] = 1) is eta0 recomputed.  |theta - theta0| <= q/2 + the ensemble's spread keeps
+// the contracted part >= 10x smaller than eta itself, which puts the tensor-core accumulation error at the level of
+// an fp32 traversal's summation noise.   stats: dim means then dim rms;  flags: [0] changed, [1] arrival ticket (0).
+__global__ void k_glm_reference(const float* __restrict__ pts, uint32_t pitch, uint32_t n, float* __restrict__ stats,
+                                float* __restrict__ theta0, int* __restrict__ flags, int force) {
     __shared__ double sm[32], sq[32];
+    __shared__ float smax[32];
+    __shared__ int last, sdiff;
+    const uint32_t dim = gridDim.x;
     const float* row = pts + (size_t)blockIdx.x * pitch;
     double s = 0.0, s2 = 0.0;
     for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) { const double v = (double)row[k]; s += v; s2 += v * v; }
@@ -415,41 +442,32 @@ __global__ void k_glm_point_mean(const float* __restrict__ pts, uint32_t pitch, 
     if (threadIdx.x == 0) {
         double t = 0.0, t2 = 0.0;
         for (uint32_t w = 0; w < (blockDim.x + 31) / 32; w++) { t += sm[w]; t2 += sq[w]; }
-        mean[blockIdx.x] = (float)(t / (double)n);
-        mean[gridDim.x + blockIdx.x] = (float)sqrt(t2 / (double)n);
+        stats[blockIdx.x] = (float)(t / (double)n);
+        stats[dim + blockIdx.x] = (float)sqrt(t2 / (double)n);
+        __threadfence();
+        last = atomicAdd(&flags[1], 1) == (int)dim - 1 ? 1 : 0;
+        sdiff = force;
     }
-}
-
-// Reference point, step 2 (one CTA): theta0 = the mean snapped to a coarse grid, q * rint(mean / q) with
-// q = 2^-3 of the largest coordinate rms (mean AND spread: while the ensemble is still wide the grid is coarse and the
-// reference stays put; once it has contracted the grid follows the size of the coefficients) rounded down to a power
-// of two.  A PURE function of the call's points (so a chain
-// restored from a checkpoint recomputes the same reference and continues bit for bit), yet stable: once the ensemble
-// has settled the snapped mean changes only when a coordinate crosses a grid line, and only then (*changed = 1) is
-// eta0 recomputed.  |theta - theta0| <= q/2 + the ensemble's spread keeps the contracted part >= 10x smaller than
-// eta itself, which puts the tensor-core accumulation error at the level of an fp32 traversal's summation noise.
-__global__ void k_glm_snap_reference(uint32_t dim, const float* __restrict__ mean, float* __restrict__ theta0,
-                                     int* __restrict__ changed, int force) {
-    __shared__ float smax[32];
-    __shared__ int sdiff;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
     float m = 0.0f;
-    for (uint32_t i = threadIdx.x; i < dim; i += blockDim.x) m = fmaxf(m, mean[dim + i]);
+    for (uint32_t i = threadIdx.x; i < dim; i += blockDim.x) m = fmaxf(m, __ldcg(stats + dim + i));
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = m;
-    if (threadIdx.x == 0) sdiff = force;
     __syncthreads();
     m = 0.0f;
     for (uint32_t w = 0; w < (blockDim.x + 31) / 32; w++) m = fmaxf(m, smax[w]);
-    // power of two not above m, times 2^-3; a non-finite or zero mean falls back to the origin
+    // power of two not above m, times 2^-3; a non-finite or zero scale falls back to the origin
     const bool usable = m > 1e-30f && m < 1e30f;
     const float q = usable ? __uint_as_float((__float_as_uint(m) & 0x7f800000u) - (3u << 23)) : 1.0f;
     for (uint32_t i = threadIdx.x; i < dim; i += blockDim.x) {
-        const float v = usable ? __fmul_rn(q, rintf(__fdiv_rn(mean[i], q))) : 0.0f;
+        const float v = usable ? __fmul_rn(q, rintf(__fdiv_rn(__ldcg(stats + i), q))) : 0.0f;
         if (v != theta0[i]) { theta0[i] = v; sdiff = 1; }
     }
     __syncthreads();
-    if (threadIdx.x == 0) *changed = sdiff;
+    if (threadIdx.x == 0) { flags[0] = sdiff; flags[1] = 0; }
 }
 
 // eta0[r] = log2(e) * (x_r . theta0), fp64 accumulation; a warp takes FOUR dataset rows [y, x_1..x_dim] at a time so

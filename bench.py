@@ -71,7 +71,7 @@ def workload(name: str):
         d, rows = 64, 10 ** 7
         m = models.logistic_regression_model(d)
         return dict(key="c4", desc="Bayesian logistic regression, D=64, 10^7 synthetic rows (BASELINE configs[3])",
-                    model=m, params=None, limits=m.limits_array(), walkers=4096, moves=1, a=1.2,
+                    model=m, params=None, limits=m.limits_array(), walkers=4096, moves=8, a=1.2,
                     cpu_walkers=512, rows=rows, cpu_rows=4000, glm=True)
     raise SystemExit(f"unknown workload {name}")
 
