@@ -261,7 +261,7 @@ struct bay_engine {
     int sm_count = 0;
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
-    uint32_t tc_configured = 0;   // GLM tensor-core kernel variants whose shared-memory opt-in is set on this device
+    uint64_t tc_configured = 0;   // kernel variants whose dynamic-shared-memory opt-in is set on this device
 };
 
 struct bay_sampler;
@@ -365,7 +365,10 @@ struct bay_sampler {
     bool glm_tc = false;
     uint32_t glm_nkc = 1;                     // 64-wide K chunks per row (DIM <= 64: 1, <= 128: 2)
     __nv_bfloat16 *glm_xh = nullptr, *glm_xl = nullptr, *glm_ah = nullptr, *glm_am = nullptr, *glm_al = nullptr;
-    int glm_terms = 4;                        // MMAs per K step: 4 = (dh+dm+dl).Xh + dh.Xl, 5 adds dm.Xl
+    int glm_terms = 3;                        // MMAs per K step: 3 = fp16 pieces (dh+dl).Xh + dh.Xl; 4 = bf16 pieces
+                                              // (dh+dm+dl).Xh + dh.Xl, 5 adds dm.Xl  (BAY_GLM_TERMS)
+    float* glm_cscale = nullptr;              // fp16 path: per column (scale, 1 / scale) of the dataset planes
+    float* glm_dscale = nullptr;              // fp16 path: {scale, 1 / scale} of the current call's delta planes
     float* glm_theta0 = nullptr;              // D: reference point of the tensor-core contraction (kernels_glm_tc.cuh)
     float* glm_eta0 = nullptr;                // rows padded to a tile: log2(e) * x_row . theta0
     float* glm_mean = nullptr;                // D: mean of the points of the current likelihood call

@@ -14,6 +14,13 @@
 //     dataset into two (Xh, Xl: a fixed 2^-17 perturbation of the data, the same for every walker), and the product is
 //     (th+tm+tl).Xh + (th+tm).Xl — five MMAs per K step (TERMS = 4 drops tm.Xl, ~2^-18 relative and zero-mean).
 //     The dataset is split ONCE into its planes (same HBM bytes as the fp32 matrix), the walker block every half-step.
+//   * TERMS = 3 — fp16 pieces (the default).  With the reference point (below) the contracted quantity delta = theta -
+//     theta0 is small and bounded, so fp16's 11-bit pieces can be used safely: delta (scaled per column by the
+//     dataset's power-of-two column scale and per call by a power of two that puts its largest entry at 2^13..2^14) in
+//     TWO pieces carries 22 bits, the dataset columns (scaled into [-1, 1]) likewise, and hi.hi + hi.lo + lo.hi —
+//     three MMAs — leaves 2^-22 relative on x.delta.  One MMA fewer than the bf16 scheme puts the kernel back on the
+//     XU (MUFU) pipe instead of the tensor pipe.  The accumulator holds (x.delta) * scale; the epilogue's FFMA
+//     a = acc / scale + eta0 undoes it.  TERMS = 4 / 5: the bf16 scheme above (BAY_GLM_TERMS=4).
 //   * REFERENCE POINT.  The tensor core does not round its fp32 accumulation to nearest: addends are aligned to the
 //     largest exponent and cut at ~2^-21 of it, so every row carries an error proportional to |eta| (measured: the
 //     error against fp64 is unchanged with bf16-exact inputs and falls 10x when |eta| is small).  The kernel therefore
@@ -36,6 +43,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -56,9 +64,11 @@ constexpr int ETA_RING = 8;                     // eta0 tiles in flight: produce
 constexpr int THREADS = (4 * NGRP + 2) * 32;    // 16 epilogue warps + TMA warp + MMA warp
 constexpr uint32_t IDESC =                      // kind::f16: D=f32, A=B=bf16, both K-major, N=128, M=128
     (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+constexpr uint32_t IDESC_F16 =                  // the same with A=B=f16
+    (1u << 4) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
 
-__host__ __device__ constexpr size_t smem_bytes(int nwb, int nkc) {
-    return 1024 /*alignment slack*/ + (size_t)nwb * nkc * 3 * TILE_BYTES + (size_t)NSTAGE * 2 * TILE_BYTES + 256 +
+__host__ __device__ constexpr size_t smem_bytes(int nwb, int nkc, int pieces = 3) {
+    return 1024 /*alignment slack*/ + (size_t)nwb * nkc * pieces * TILE_BYTES + (size_t)NSTAGE * 2 * TILE_BYTES + 256 +
            (size_t)ETA_RING * TILE * 4;
 }
 
@@ -96,11 +106,15 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+template <uint32_t DESC>
+__device__ __forceinline__ void tc_mma_f16kind(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
     asm volatile(
         "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(DESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    tc_mma_f16kind<IDESC>(tmem_d, adesc, bdesc, accumulate);
 }
 // K-major, SWIZZLE_128B operand tile (rows of 128 B, 8-row atoms of 1024 B): SBO = 1024 B, version 1, layout 2.
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
@@ -153,13 +167,15 @@ template <int NWB, int NKC, int LINK, int TERMS>
 __global__ void __launch_bounds__(THREADS, 1)  // (NWB, NKC) in {1, 2} x {1}, {1} x {2}
 k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                 const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_am,
-                const __grid_constant__ CUtensorMap map_al, const float* __restrict__ eta0, const uint32_t rows,
-                const uint32_t n_tiles, const uint32_t groups, double* __restrict__ partial, const uint32_t ldp) {
+                const __grid_constant__ CUtensorMap map_al, const float* __restrict__ eta0,
+                const float* __restrict__ dscale, const uint32_t rows, const uint32_t n_tiles, const uint32_t groups,
+                double* __restrict__ partial, const uint32_t ldp) {
+    constexpr int PIECES = TERMS == 3 ? 2 : 3;              // planes of the walker block: fp16 (hi, lo) or bf16 (hi, mid, lo)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* a_hi = smem;                                   // NWB x NKC tiles, tile (wb, kc) at wb*NKC + kc
-    uint8_t* a_mi = a_hi + NWB * NKC * TILE_BYTES;
-    uint8_t* a_lo = a_mi + NWB * NKC * TILE_BYTES;
+    uint8_t* a_mi = a_hi + NWB * NKC * TILE_BYTES;          // (absent with two pieces)
+    uint8_t* a_lo = a_hi + (PIECES - 1) * NWB * NKC * TILE_BYTES;
     uint8_t* b_base = a_lo + NWB * NKC * TILE_BYTES;        // NSTAGE x (hi, lo)
     uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + NSTAGE * 2 * TILE_BYTES);
     uint64_t* full_bar = bars;                              // [NSTAGE] TMA -> MMA
@@ -192,12 +208,12 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
     if (warp == 4 * NGRP) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            mbar_expect_tx(a_bar, NWB * NKC * 3 * TILE_BYTES);
+            mbar_expect_tx(a_bar, NWB * NKC * PIECES * TILE_BYTES);
             for (int wb = 0; wb < NWB; wb++)
                 for (int kc = 0; kc < NKC; kc++) {
                     const int wrow = (int)((g * NWB + wb) * TILE);
                     tma_load_2d(a_hi + (wb * NKC + kc) * TILE_BYTES, &map_ah, kc * KD, wrow, a_bar);
-                    tma_load_2d(a_mi + (wb * NKC + kc) * TILE_BYTES, &map_am, kc * KD, wrow, a_bar);
+                    if (PIECES == 3) tma_load_2d(a_mi + (wb * NKC + kc) * TILE_BYTES, &map_am, kc * KD, wrow, a_bar);
                     tma_load_2d(a_lo + (wb * NKC + kc) * TILE_BYTES, &map_al, kc * KD, wrow, a_bar);
                 }
             for (uint32_t it = 0; it < my_tiles; it++) {
@@ -244,6 +260,15 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                         const uint64_t am = make_desc(smem_u32(a_mi + (wb * NKC + kc) * TILE_BYTES));
                         const uint64_t al = make_desc(smem_u32(a_lo + (wb * NKC + kc) * TILE_BYTES));
                         // smallest products first: they enter the fp32 accumulator before the leading term does
+                        if (TERMS == 3) {   // fp16 pieces: lo.hi + hi.lo + hi.hi
+#pragma unroll
+                            for (int k = 0; k < KD / 16; k++) tc_mma_f16kind<IDESC_F16>(d, al + 2 * k, bh[kc] + 2 * k, kc > 0 || k > 0);
+#pragma unroll
+                            for (int k = 0; k < KD / 16; k++) tc_mma_f16kind<IDESC_F16>(d, ah + 2 * k, bl[kc] + 2 * k, 1);
+#pragma unroll
+                            for (int k = 0; k < KD / 16; k++) tc_mma_f16kind<IDESC_F16>(d, ah + 2 * k, bh[kc] + 2 * k, 1);
+                            continue;
+                        }
 #pragma unroll
                         for (int k = 0; k < KD / 16; k++) tc_mma_bf16(d, al + 2 * k, bh[kc] + 2 * k, kc > 0 || k > 0);   // lo*hi
                         if (TERMS >= 5) {
@@ -280,6 +305,7 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         // leaves MUFU.EX2(-|a|), one FFMA on the running product and one FADD on sum|a|.
         // Rows that TMA zero-filled past the end of the dataset give a = 0 exactly: no |a|, factor 2 -> corrected
         // by subtracting (TILE - valid) from the log2 sum.
+        const float inv_scale = TERMS == 3 ? __ldg(dscale + 1) : 1.0f;   // fp16 pieces: accumulators hold (x.delta) * scale
         float hi = 0.f, lo = 0.f;                        // two-float (compensated) sum over this thread's items
         for (uint32_t item = grp; item < n_items; item += NACC) {
             const uint32_t it = item / NWB;
@@ -298,8 +324,8 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
                     float4 eta;
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                  : "=f"(eta.x), "=f"(eta.y), "=f"(eta.z), "=f"(eta.w) : "r"(eta_tile + (c + j) * 4u));
-                    const float a0 = __uint_as_float(r[j]) + eta.x, a1 = __uint_as_float(r[j + 1]) + eta.y;
-                    const float a2 = __uint_as_float(r[j + 2]) + eta.z, a3 = __uint_as_float(r[j + 3]) + eta.w;
+                    const float a0 = fmaf(__uint_as_float(r[j]), inv_scale, eta.x), a1 = fmaf(__uint_as_float(r[j + 1]), inv_scale, eta.y);
+                    const float a2 = fmaf(__uint_as_float(r[j + 2]), inv_scale, eta.z), a3 = fmaf(__uint_as_float(r[j + 3]), inv_scale, eta.w);
                     if (LINK == 1) {   // sum of 2^a = exp(eta)
                         m0 += ex2_approx(a0); m1 += ex2_approx(a1);
                         m2 += ex2_approx(a2); m3 += ex2_approx(a3);
@@ -425,7 +451,8 @@ __global__ void k_glm_finish_tc(const __grid_constant__ FinishPlan plan, uint32_
 // bit for bit), yet stable: once the ensemble has settled the snapped mean changes only when a coordinate crosses a
 // grid line, and only then (flags[0] = 1) is eta0 recomputed.  |theta - theta0| <= q/2 + the ensemble's spread keeps
 // the contracted part >= 10x smaller than eta itself, which puts the tensor-core accumulation error at the level of
-// an fp32 traversal's summation noise.   stats: dim means then dim rms;  flags: [0] changed, [1] arrival ticket (0).
+// an fp32 traversal's summation noise.   stats: dim means then dim rms;  flags: [0] changed, [1] arrival ticket (0),
+// [2] reset to 0 for the fp16 path's delta maximum.
 __global__ void k_glm_reference(const float* __restrict__ pts, uint32_t pitch, uint32_t n, float* __restrict__ stats,
                                 float* __restrict__ theta0, int* __restrict__ flags, int force) {
     __shared__ double sm[32], sq[32];
@@ -467,7 +494,7 @@ __global__ void k_glm_reference(const float* __restrict__ pts, uint32_t pitch, u
         if (v != theta0[i]) { theta0[i] = v; sdiff = 1; }
     }
     __syncthreads();
-    if (threadIdx.x == 0) { flags[0] = sdiff; flags[1] = 0; }
+    if (threadIdx.x == 0) { flags[0] = sdiff; flags[1] = 0; flags[2] = 0; }   // [2]: this call's delta maximum (float bits)
 }
 
 // eta0[r] = log2(e) * (x_r . theta0), fp64 accumulation; a warp takes FOUR dataset rows [y, x_1..x_dim] at a time so
@@ -499,6 +526,90 @@ __global__ void k_glm_eta0(const float* __restrict__ data, uint64_t rows, uint32
             eta0[r0 + lane] = (float)(v * 1.4426950408889634);
         }
     }
+}
+
+// ---- fp16 pieces (TERMS = 3) ----------------------------------------------------------------------------------------
+// column scales: colmax[i] = max_rows |x_ri| as float bits (atomicMax on the non-negative pattern)
+__global__ void k_glm_colmax(const float* __restrict__ data, uint64_t rows, uint32_t dim, uint32_t* __restrict__ colmax) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    float m[4] = {0.f, 0.f, 0.f, 0.f};                      // dims lane, lane + 32, ... (dim <= 128)
+    for (uint64_t r = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < rows; r += warps) {
+        const float* row = data + r * (dim + 1) + 1;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (lane + 32u * q < dim) m[q] = fmaxf(m[q], fabsf(__ldcs(row + lane + 32u * q)));
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        if (lane + 32u * q < dim && m[q] > 0.f) atomicMax(&colmax[lane + 32u * q], __float_as_uint(m[q]));
+}
+
+// cscale[i] = the power of two that brings column i of x * log2(e) into [-1, 1] (1 for an all-zero column); stored as
+// (cscale, 1 / cscale) pairs
+__global__ void k_glm_colscale(uint32_t dim, const uint32_t* __restrict__ colmax, float* __restrict__ cscale) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dim) return;
+    const float m = __uint_as_float(colmax[i]) * LOG2E;
+    uint32_t e = (__float_as_uint(m) >> 23) & 0xffu;        // m in [2^(e-127), 2^(e-126))
+    if (!(m > 0.f) || e == 0u || e > 250u) { cscale[2 * i] = 1.0f; cscale[2 * i + 1] = 1.0f; return; }
+    cscale[2 * i] = __uint_as_float((253u - e) << 23);      // 2^(126-e): m * cscale in [1/2, 1)
+    cscale[2 * i + 1] = __uint_as_float((e + 1u) << 23);    // 2^(e-126)
+}
+
+// dataset rows -> fp16 hi/lo planes [rows][kdp] of x * log2(e) * cscale[i], zero-padded past dim
+__global__ void k_glm_split_rows_f16(const float* __restrict__ data, uint64_t rows, uint32_t dim, uint32_t kdp,
+                                     const float* __restrict__ cscale, __half* __restrict__ hi, __half* __restrict__ lo) {
+    const uint64_t total = rows * kdp;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const uint64_t r = e / kdp;
+        const uint32_t i = (uint32_t)(e % kdp);
+        const float x = i < dim ? __fmul_rn(__fmul_rn(data[r * (dim + 1) + 1 + i], LOG2E), cscale[2 * i]) : 0.0f;
+        const __half h = __float2half_rn(x);
+        hi[e] = h;
+        lo[e] = __float2half_rn(x - __half2float(h));
+    }
+}
+
+// largest |(theta - theta0)_i / cscale_i| over the call's points, as float bits into *dmax (reset by the caller)
+__global__ void k_glm_delta_max(const float* __restrict__ pts, uint32_t pitch, uint32_t n, uint32_t dim,
+                                const float* __restrict__ theta0, const float* __restrict__ cscale,
+                                uint32_t* __restrict__ dmax) {
+    float m = 0.f;
+    const uint64_t total = (uint64_t)n * dim, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const uint32_t i = (uint32_t)(e / n), k = (uint32_t)(e % n);      // coalesced along the points
+        m = fmaxf(m, fabsf(__fmul_rn(__fsub_rn(pts[(size_t)i * pitch + k], theta0[i]), cscale[2 * i + 1])));
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(dmax, __float_as_uint(m));   // NaN / inf points: see below
+}
+
+// points -> fp16 hi/lo planes [n][kdp] of delta' = (theta - theta0) / cscale_i * scale, scale = the power of two that
+// puts the largest |delta'| of the call at 2^13..2^14 (fp16 overflows at 65504); dscale = {scale, 1 / scale}.
+// A non-finite point makes the maximum non-finite: scale falls back to 1 and that walker's row goes non-finite,
+// which the accept test rejects — like the generic kernel.
+__global__ void k_glm_split_points_f16(const float* __restrict__ pts, uint32_t pitch, uint32_t n, uint32_t dim,
+                                       uint32_t kdp, const float* __restrict__ theta0, const float* __restrict__ cscale,
+                                       const uint32_t* __restrict__ dmax, float* __restrict__ dscale,
+                                       __half* __restrict__ hi, __half* __restrict__ lo) {
+    const float m = __uint_as_float(*dmax);
+    const uint32_t em = (__float_as_uint(m) >> 23) & 0xffu;
+    float scale = 1.0f, inv = 1.0f;
+    if (m > 0.f && em >= 20u && em <= 230u) {                // m in [2^(em-127), 2^(em-126)) -> m * scale in [2^13, 2^14)
+        scale = __uint_as_float((267u - em) << 23);          // 2^(140-em)
+        inv = __uint_as_float((em - 13u) << 23);             // 2^(em-140)
+    }
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0) { dscale[0] = scale; dscale[1] = inv; }
+    if (e >= (uint64_t)n * kdp) return;
+    const uint32_t k = (uint32_t)(e / kdp), i = (uint32_t)(e % kdp);
+    const float x = i < dim ? __fmul_rn(__fmul_rn(__fsub_rn(pts[(size_t)i * pitch + k], theta0[i]), cscale[2 * i + 1]), scale) : 0.0f;
+    const __half h = __float2half_rn(x);
+    hi[e] = h;
+    lo[e] = __float2half_rn(x - __half2float(h));
 }
 
 // dataset rows [y, x_1..x_dim] (stride dim + 1) -> bf16 hi/lo planes [rows][kdp] of x * log2(e), zero-padded past dim
