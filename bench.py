@@ -513,7 +513,7 @@ def main():
         n_groups = -(-(W // 2) // per)
         per_launch_ms = per_launch_ms / n_groups
         flops_per_launch = 2.0 * (wl["rows"] / (world if sharded else 1)) * D * min(W // 2, per)   # per GPU
-        terms = 5 if os.environ.get("BAY_GLM_TERMS") == "5" else 4
+        terms = {"4": 4, "5": 5}.get(os.environ.get("BAY_GLM_TERMS", ""), 3)
         peak = float(peaks["bf16_tflops_sustained"]) if peaks else 1400.0
         achieved = flops_per_launch / (per_launch_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
@@ -521,10 +521,11 @@ def main():
                 "flops_per_launch": flops_per_launch,
                 "launch_us": per_launch_ms * 1e3,
                 "executed_mma_tflops": terms * achieved, "mma_terms": terms, "executed_frac": terms * achieved / peak,
-                "note": "achieved counts ALGORITHMIC flops (2*rows*D per walker).  An accept test on 10^7 rows needs the "
-                        "coefficients represented exactly: theta is split into three bf16 pieces and the dataset into "
-                        f"two, {terms} MMAs per product, so the tensor pipe executes {terms}x the algorithmic flops and frac "
-                        f"cannot exceed 1/{terms}; see DESIGN.md 4.2 for the pipe utilisations ncu reports",
+                "note": "achieved counts ALGORITHMIC flops (2*rows*D per walker).  fp32-level accuracy on 16-bit tensor-core "
+                        f"inputs takes {terms} MMAs per product (theta - theta0 and the dataset in two fp16 pieces each; three "
+                        "bf16 pieces of theta with BAY_GLM_TERMS=4), so the tensor pipe executes that multiple of the "
+                        f"algorithmic flops and frac cannot exceed 1/{terms}; the kernel's binding unit is the XU (exp2) pipe, "
+                        "see DESIGN.md 4.2 for the pipe utilisations ncu reports",
                 "hbm_view": {"bytes_per_launch": flops_per_launch / min(W // 2, per) * 2.0,
                              "achieved_GBps": flops_per_launch / min(W // 2, per) * 2.0 / (per_launch_ms * 1e-3) / 1e9,
                              "note": "dataset bytes (bf16 hi+lo planes = 4 B/element) streamed from HBM once per launch"}}
@@ -575,7 +576,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
                 "scaling": "strong" if (wl.get("glm") or args.strong) else "weak", "vs_baseline": None,
-                "dtype": "f32 (tensor cores on bf16 pieces: theta in 3, dataset in 2, 4 MMAs per product, fp32 accumulate)"
+                "dtype": "f32 (tensor cores on fp16 pieces: theta - theta0 and the dataset in 2 each, 3 MMAs per product, fp32 accumulate)"
                          if wl.get("glm") else ("f32 (tensor cores on fp16 hi/lo pieces, fp32 accumulate)"
                                                 if sampler.uses_quadform() else "f32"),
                 "data": "synthetic",
