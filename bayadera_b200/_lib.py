@@ -7,11 +7,13 @@ when no CUDA device is present.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
-LIB_PATH = Path(__file__).resolve().parent / "libbayadera_b200.so"
+# BAYADERA_B200_LIB: an alternative build of the same library (kernel experiments); default = the in-tree build
+LIB_PATH = Path(os.environ.get("BAYADERA_B200_LIB") or Path(__file__).resolve().parent / "libbayadera_b200.so")
 
 OK, EINVAL, EINVAL_WALKERS, EACOR_TOO_SHORT, ECOMPILE, ECUDA, ENCCL, ENOTSUP = 0, -1, -2, -3, -4, -5, -6, -7
 

@@ -399,6 +399,98 @@ __global__ void __launch_bounds__(512) k_hist_aos(const float* __restrict__ data
     }
 }
 
+// The same histogram WITHOUT shared-memory atomics.  ATOMS retires a conflict-free warp instruction only every ~12
+// clocks, which capped k_hist_aos at a quarter of the HBM rate.  Here every WARP owns a private [bins][32] block of
+// counters and every LANE a fixed column of it (counter (bin, lane) sits in bank `lane`), so an increment is a plain
+// conflict-free LDS / IADD / STS and no two threads ever touch the same counter.  R rows are in flight per lane: the R
+// loads are issued back to back and each row stores count + (number of the R rows that fell into the same bin), the
+// same value from every row of an equal group, so the order of the stores does not matter.
+// A CTA works on ONE chunk of <= 32 dimensions (plan.first[c] .. plan.first[c+1] are the CTAs of chunk c, in numbers
+// proportional to the chunk's cost).  A chunk narrower than 32 (the tail of D = 100, or a 1- or 2-dimensional model)
+// packs 32 / tp rows into one warp instruction, tp = the next power of two >= its width.
+struct HistPlan {
+    uint32_t chunks;
+    uint32_t first[34];     // CTA index where chunk c starts; first[chunks] = gridDim.x
+};
+
+template <int R>
+__global__ void __launch_bounds__(512) k_hist_aos_lanes(const float* __restrict__ data, uint64_t offset, uint64_t ld,
+                                                        uint32_t dim, uint64_t n, const float* __restrict__ limits,
+                                                        uint32_t bins, const __grid_constant__ HistPlan plan,
+                                                        uint32_t* __restrict__ counts) {
+    extern __shared__ uint32_t sh[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t chunk = 0;
+    while (chunk + 1 < plan.chunks && blockIdx.x >= plan.first[chunk + 1]) chunk++;
+    const uint32_t slot = blockIdx.x - plan.first[chunk], nslots = plan.first[chunk + 1] - plan.first[chunk];
+    const uint32_t d0 = 32u * chunk, width = min(32u, dim - d0);
+    uint32_t tp = 1;
+    while (tp < width) tp <<= 1;
+    const uint32_t rpw = 32u / tp, rsub = lane / tp, dl = lane & (tp - 1);
+    const bool active = dl < width;
+    {
+        uint4* z = reinterpret_cast<uint4*>(sh);
+        for (uint32_t i = threadIdx.x; i < nw * bins * 8u; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    const uint32_t d = d0 + (active ? dl : 0u);
+    const float lo = limits[2 * d], range = __fsub_rn(limits[2 * d + 1], lo);
+    const float fbins = (float)bins, guard = fbins - 0.5f, scale = __fdividef(fbins, range);
+    __syncthreads();
+    uint32_t* mine = sh + warp * bins * 32u + lane;
+    // rows of this CTA: [r_begin, r_end); a warp step covers R * rpw consecutive rows, the warps interleave
+    const uint64_t r_begin = n * slot / nslots, r_end = n * (slot + 1) / nslots;
+    const uint64_t step = (uint64_t)R * rpw;
+    const float* base = data + offset + d;
+    float v[R], vn[R];
+    auto fetch = [&](float (&x)[R], uint64_t row) {
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            const uint64_t r = row + (uint64_t)k * rpw + rsub;
+            x[k] = (active && r < r_end) ? __ldcs(base + ld * r) : 0.f;
+        }
+    };
+    uint64_t row = r_begin + warp * step;
+    if (row < r_end) fetch(v, row);
+    for (; row < r_end; row += nw * step) {
+        const uint64_t next = row + nw * step;
+        if (next < r_end) fetch(vn, next);
+        if (next + 8 * nw * step < r_end && active)     // keep HBM busy well ahead of the few resident warps
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ld * (next + 8 * nw * step + rsub)));
+        uint32_t b[R], c[R];
+        bool ok[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            ok[k] = active && row + (uint64_t)k * rpw + rsub < r_end;
+            b[k] = ok[k] ? hist_bin(v[k], lo, range, fbins, bins, scale, guard) : bins + k;   // sentinels never match
+        }
+#pragma unroll
+        for (int k = 0; k < R; k++) c[k] = mine[(ok[k] ? b[k] : 0u) * 32u];
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            uint32_t same = 1;
+#pragma unroll
+            for (int j = 0; j < R; j++)
+                if (j != k) same += (b[j] == b[k]) ? 1u : 0u;
+            c[k] += same;
+        }
+#pragma unroll
+        for (int k = 0; k < R; k++)
+            if (ok[k]) mine[b[k] * 32u] = c[k];
+#pragma unroll
+        for (int k = 0; k < R; k++) v[k] = vn[k];
+    }
+    __syncthreads();
+    // fold the warps (and, in a narrow chunk, the lanes that served the same dimension); one global atomic per non-empty bin
+    for (uint32_t i = threadIdx.x; i < bins * tp; i += blockDim.x) {
+        const uint32_t bin = i / tp, x = i & (tp - 1);
+        if (x >= width) continue;
+        uint32_t total = 0;
+        for (uint32_t w = 0; w < nw; w++)
+            for (uint32_t q = 0; q < rpw; q++) total += sh[(w * bins + bin) * 32u + q * tp + x];
+        if (total) atomicAdd(&counts[(size_t)bins * (d0 + x) + bin], total);
+    }
+}
+
 // uint_to_real (estimate.cu:34-44): pdf = (alpha / (hi-lo)) * count
 __global__ void k_uint_to_real(uint32_t bins, uint32_t dim, float alpha,
                                const float* __restrict__ limits,

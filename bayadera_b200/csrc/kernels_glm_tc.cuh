@@ -133,6 +133,64 @@ __device__ __forceinline__ float lg2_approx(float x) {
     return y;
 }
 
+// Packed fp32 pairs (FFMA2 / FADD2: one issue slot for two lanes' worth of work) — the epilogue is bound by issue
+// slots and the XU pipe, not by the FMA pipe.
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// 2^-|a| for a PAIR on the FMA pipe instead of the XU pipe: x = max(-|a|, -126) = n + f with n = round(x), f in
+// [-1/2, 1/2]; 2^f by a degree-5 minimax polynomial (relative error 7.5e-8, below MUFU.EX2's 2^-22), n added to the
+// exponent field.  1.5 * 2^23 as the rounding constant: the low mantissa bits of x + magic hold n in two's complement.
+// BAY_GLM_POLY8 = elements out of every 8 that take the polynomial (0, 2 or 4); the rest take MUFU.EX2.
+// MEASURED (profiles/r02_c4_epilogue_variants.txt): with 2 of 8 the kernel needs 4.3 % fewer cycles (XU pipe 86 % ->
+// 69 %) and the SM clock settles 4.4 % lower: the kernel runs at the board's power cap (sw_power_cap, ~1.5 of 1.97
+// GHz), where cycles saved on one pipe by spending more instructions on another buy nothing.  Default: 0.
+#ifndef BAY_GLM_POLY8
+#define BAY_GLM_POLY8 0
+#endif
+__device__ __forceinline__ uint64_t ex2_neg_abs_poly2(float a0, float a1) {
+    const float x0 = fmaxf(-fabsf(a0), -126.f), x1 = fmaxf(-fabsf(a1), -126.f);
+    const uint64_t magic = pk2(12582912.f, 12582912.f);
+    const uint64_t x = pk2(x0, x1);
+    const uint64_t t = add2(x, magic);
+    const uint64_t f = sub2(x, sub2(t, magic));
+    uint64_t p = pk2(0x1.5c08b6p-10f, 0x1.5c08b6p-10f);
+    p = fma2(p, f, pk2(0x1.3d0c4ap-7f, 0x1.3d0c4ap-7f));
+    p = fma2(p, f, pk2(0x1.c6b6e6p-5f, 0x1.c6b6e6p-5f));
+    p = fma2(p, f, pk2(0x1.ebf918p-3f, 0x1.ebf918p-3f));
+    p = fma2(p, f, pk2(0x1.62e428p-1f, 0x1.62e428p-1f));
+    p = fma2(p, f, pk2(0x1.000002p+0f, 0x1.000002p+0f));
+    uint32_t p0, p1, n0, n1;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(p0), "=r"(p1) : "l"(p));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(n0), "=r"(n1) : "l"(t));
+    return pk2u(p0 + (n0 << 23), p1 + (n1 << 23));
+}
+
 #define BAY_TMEM_LD32(r, taddr)                                                                              \
     asm volatile(                                                                                            \
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                            \
@@ -306,6 +364,7 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
         // Rows that TMA zero-filled past the end of the dataset give a = 0 exactly: no |a|, factor 2 -> corrected
         // by subtracting (TILE - valid) from the log2 sum.
         const float inv_scale = TERMS == 3 ? __ldg(dscale + 1) : 1.0f;   // fp16 pieces: accumulators hold (x.delta) * scale
+        const uint64_t inv_scale2 = pk2(inv_scale, inv_scale);
         float hi = 0.f, lo = 0.f;                        // two-float (compensated) sum over this thread's items
         for (uint32_t item = grp; item < n_items; item += NACC) {
             const uint32_t it = item / NWB;
@@ -314,27 +373,42 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
             mbar_wait(&tfull_bar[grp], (item / NACC) & 1u);
             tc_fence_after();
             // four independent (product, |a|-sum) chains; the next 16 columns are in flight while 16 are reduced
-            float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, p0 = 1.f, p1 = 1.f, p2 = 1.f, p3 = 1.f;
+            float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+            uint64_t pa = pk2(1.f, 1.f), pb = pa;        // four product chains in two packed pairs
             uint32_t ra[16], rb[16];
             const uint32_t eta_tile = eta_s + (it % ETA_RING) * TILE * 4u;
             // a = eta0[row] + (x . delta): the reference part is added here, in round-to-nearest fp32
             auto reduce = [&](const uint32_t (&r)[16], const uint32_t c) {
+                if (LINK == 1) {   // sum of 2^a = exp(eta)
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    float4 eta;
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(eta.x), "=f"(eta.y), "=f"(eta.z), "=f"(eta.w) : "r"(eta_tile + (c + j) * 4u));
-                    const float a0 = fmaf(__uint_as_float(r[j]), inv_scale, eta.x), a1 = fmaf(__uint_as_float(r[j + 1]), inv_scale, eta.y);
-                    const float a2 = fmaf(__uint_as_float(r[j + 2]), inv_scale, eta.z), a3 = fmaf(__uint_as_float(r[j + 3]), inv_scale, eta.w);
-                    if (LINK == 1) {   // sum of 2^a = exp(eta)
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 eta;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(eta.x), "=f"(eta.y), "=f"(eta.z), "=f"(eta.w) : "r"(eta_tile + (c + j) * 4u));
+                        const float a0 = fmaf(__uint_as_float(r[j]), inv_scale, eta.x), a1 = fmaf(__uint_as_float(r[j + 1]), inv_scale, eta.y);
+                        const float a2 = fmaf(__uint_as_float(r[j + 2]), inv_scale, eta.z), a3 = fmaf(__uint_as_float(r[j + 3]), inv_scale, eta.w);
                         m0 += ex2_approx(a0); m1 += ex2_approx(a1);
                         m2 += ex2_approx(a2); m3 += ex2_approx(a3);
-                    } else {
-                        const float e0 = fabsf(a0), e1 = fabsf(a1);
-                        const float e2 = fabsf(a2), e3 = fabsf(a3);
-                        const float t0 = ex2_approx(-e0), t1 = ex2_approx(-e1), t2 = ex2_approx(-e2), t3 = ex2_approx(-e3);
-                        p0 = fmaf(p0, t0, p0); p1 = fmaf(p1, t1, p1); p2 = fmaf(p2, t2, p2); p3 = fmaf(p3, t3, p3);
-                        m0 += e0; m1 += e1; m2 += e2; m3 += e3;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 8) {
+                        uint64_t eta[4], t[4];
+                        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(eta[0]), "=l"(eta[1]) : "r"(eta_tile + (c + j) * 4u));
+                        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(eta[2]), "=l"(eta[3]) : "r"(eta_tile + (c + j + 4) * 4u));
+                        float a[8];
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            upk2(fma2(pk2u(r[j + 2 * q], r[j + 2 * q + 1]), inv_scale2, eta[q]), a[2 * q], a[2 * q + 1]);
+                        m0 += fabsf(a[0]); m1 += fabsf(a[1]); m2 += fabsf(a[2]); m3 += fabsf(a[3]);
+                        m0 += fabsf(a[4]); m1 += fabsf(a[5]); m2 += fabsf(a[6]); m3 += fabsf(a[7]);
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {   // the LAST BAY_GLM_POLY8 / 2 pairs go to the FMA pipe
+                            if (q >= 4 - BAY_GLM_POLY8 / 2) t[q] = ex2_neg_abs_poly2(a[2 * q], a[2 * q + 1]);
+                            else t[q] = pk2(ex2_approx(-fabsf(a[2 * q])), ex2_approx(-fabsf(a[2 * q + 1])));
+                        }
+                        pa = fma2(pa, t[0], pa); pb = fma2(pb, t[1], pb);
+                        pa = fma2(pa, t[2], pa); pb = fma2(pb, t[3], pb);
                     }
                 }
             };
@@ -362,6 +436,9 @@ k_glm_loglik_tc(const __grid_constant__ CUtensorMap map_xh, const __grid_constan
             if (LINK == 1) {
                 x = ((m0 + m1) + (m2 + m3)) - (float)(TILE - valid);
             } else {
+                float p0, p1, p2, p3;
+                upk2(pa, p0, p1);
+                upk2(pb, p2, p3);
                 const float lg = (lg2_approx(p0 * p1) + lg2_approx(p2 * p3)) - (float)(TILE - valid);
                 x = fmaf(0.5f, (m0 + m1) + (m2 + m3), lg);
             }
