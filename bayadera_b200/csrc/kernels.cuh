@@ -399,12 +399,13 @@ __global__ void __launch_bounds__(512) k_hist_aos(const float* __restrict__ data
     }
 }
 
-// The same histogram WITHOUT shared-memory atomics.  ATOMS retires a conflict-free warp instruction only every ~12
+// The same histogram WITHOUT shared-memory atomics.  ATOMS retires a conflict-free warp instruction only every ~24
 // clocks, which capped k_hist_aos at a quarter of the HBM rate.  Here every WARP owns a private [bins][32] block of
-// counters and every LANE a fixed column of it (counter (bin, lane) sits in bank `lane`), so an increment is a plain
-// conflict-free LDS / IADD / STS and no two threads ever touch the same counter.  R rows are in flight per lane: the R
-// loads are issued back to back and each row stores count + (number of the R rows that fell into the same bin), the
-// same value from every row of an equal group, so the order of the stores does not matter.
+// 16-bit counters and every LANE a fixed column of it, so an increment is a plain LDS / IADD / STS and no two threads
+// ever touch the same counter.  R rows are in flight per lane: the R loads are issued back to back and each row stores
+// count + (number of the R rows that fell into the same bin) — the same value from every row of an equal group, so
+// the order of the stores does not matter.  16-bit counters double the resident warps (latency is what binds a
+// kernel of 25 dependent instructions per row); the host keeps a CTA's rows <= 65535 so that none can overflow.
 // A CTA works on ONE chunk of <= 32 dimensions (plan.first[c] .. plan.first[c+1] are the CTAs of chunk c, in numbers
 // proportional to the chunk's cost).  A chunk narrower than 32 (the tail of D = 100, or a 1- or 2-dimensional model)
 // packs 32 / tp rows into one warp instruction, tp = the next power of two >= its width.
@@ -413,12 +414,32 @@ struct HistPlan {
     uint32_t first[34];     // CTA index where chunk c starts; first[chunks] = gridDim.x
 };
 
-template <int R>
+// hist_bin in fixed point, for bins <= 256: q = round(t' * 4096) comes out of ONE FFMA against the rounding constant
+// 1.5 * 2^23 (no F2I / FRND, which run on the quarter-rate XU pipe).  The fast path is taken when t' is inside
+// [0.5, bins - 0.5) and q is not a multiple of 4096, i.e. t' is at least 1 / 8192 = 1.2e-4 away from an integer —
+// the approximate t' is within 1.8e-7 relative (4.6e-5 at the top bin) of the defining value, so floor(t') is the
+// bin; everything else (1 value in 4096, NaN, out of range) takes the exact path.
+constexpr float HIST_FX = 4096.f;
+__device__ __forceinline__ bool hist_fx_plain(uint32_t q, uint32_t span) { return (q - 2048u) < span && (q & 4095u) != 0u; }
+__device__ __forceinline__ uint32_t hist_bin_fx(float x, float lo, float range, float fbins, uint32_t bins, float scale_fx) {
+    const float d = __fsub_rn(x, lo);
+    const uint32_t q = __float_as_uint(fmaf(d, scale_fx, 12582912.f)) - 0x4B400000u;
+    if (__builtin_expect(hist_fx_plain(q, bins * 4096u - 4096u), 1)) return q >> 12;
+    return hist_bin_exact(d, range, fbins, bins);
+}
+
+__device__ __noinline__ uint32_t hist_bin_fx_call(float x, float lo, float range, float fbins, uint32_t bins, float scale_fx) {
+    return hist_bin_fx(x, lo, range, fbins, bins, scale_fx);
+}
+
+template <int R, int G>   // R rows per shared-memory round, G rounds per load step: R * G rows in flight per lane
 __global__ void __launch_bounds__(512) k_hist_aos_lanes(const float* __restrict__ data, uint64_t offset, uint64_t ld,
                                                         uint32_t dim, uint64_t n, const float* __restrict__ limits,
                                                         uint32_t bins, const __grid_constant__ HistPlan plan,
                                                         uint32_t* __restrict__ counts) {
+    constexpr int RL = R * G;
     extern __shared__ uint32_t sh[];
+    uint16_t* sh16 = reinterpret_cast<uint16_t*>(sh);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     uint32_t chunk = 0;
     while (chunk + 1 < plan.chunks && blockIdx.x >= plan.first[chunk + 1]) chunk++;
@@ -430,41 +451,40 @@ __global__ void __launch_bounds__(512) k_hist_aos_lanes(const float* __restrict_
     const bool active = dl < width;
     {
         uint4* z = reinterpret_cast<uint4*>(sh);
-        for (uint32_t i = threadIdx.x; i < nw * bins * 8u; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = threadIdx.x; i < nw * bins * 4u; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
     }
     const uint32_t d = d0 + (active ? dl : 0u);
     const float lo = limits[2 * d], range = __fsub_rn(limits[2 * d + 1], lo);
-    const float fbins = (float)bins, guard = fbins - 0.5f, scale = __fdividef(fbins, range);
+    const float fbins = (float)bins, scale_fx = __fdividef(fbins * HIST_FX, range);
+    const uint32_t span = bins * 4096u - 4096u;
     __syncthreads();
-    uint32_t* mine = sh + warp * bins * 32u + lane;
-    // rows of this CTA: [r_begin, r_end); a warp step covers R * rpw consecutive rows, the warps interleave
-    const uint64_t r_begin = n * slot / nslots, r_end = n * (slot + 1) / nslots;
-    const uint64_t step = (uint64_t)R * rpw;
-    const float* base = data + offset + d;
-    float v[R], vn[R];
-    auto fetch = [&](float (&x)[R], uint64_t row) {
+    uint16_t* mine = sh16 + warp * bins * 32u + lane;
+    // rows of this CTA: [r_begin, r_begin + rows), rows <= 65535 and rows * ld * 4 < 2^32 (the host sees to both).
+    // A warp step covers `step` = RL * rpw consecutive rows; every warp owns a CONTIGUOUS run of full steps (so that
+    // it can prefetch its own stream), and the last warp also takes the ragged rest, row by row.
+    const uint64_t r_begin = n * slot / nslots;
+    const uint32_t rows = (uint32_t)(n * (slot + 1) / nslots - r_begin);
+    const uint32_t step = (uint32_t)RL * rpw, full = rows / step;
+    const uint32_t per_warp = (full + nw - 1) / nw;
+    const uint32_t s_begin = min(full, warp * per_warp), s_end = min(full, s_begin + per_warp);
+    const char* cta = reinterpret_cast<const char*>(data + offset + ld * r_begin + d0);   // row 0, first dimension of the chunk
+    const uint32_t ldb = (uint32_t)ld * 4u;                            // bytes per row
+    const uint32_t pitch = ldb * rpw, hop = ldb * step;                // a lane's next row / the next step
+    auto count_rows = [&](const float* x) {     // R rows of this lane -> its private counters
+        uint32_t q[R], b[R], c[R];
+        bool plain = true;
 #pragma unroll
         for (int k = 0; k < R; k++) {
-            const uint64_t r = row + (uint64_t)k * rpw + rsub;
-            x[k] = (active && r < r_end) ? __ldcs(base + ld * r) : 0.f;
+            q[k] = __float_as_uint(fmaf(__fsub_rn(x[k], lo), scale_fx, 12582912.f)) - 0x4B400000u;
+            plain = plain && hist_fx_plain(q[k], span);
+            b[k] = (q[k] >> 12) * 32u;
         }
-    };
-    uint64_t row = r_begin + warp * step;
-    if (row < r_end) fetch(v, row);
-    for (; row < r_end; row += nw * step) {
-        const uint64_t next = row + nw * step;
-        if (next < r_end) fetch(vn, next);
-        if (next + 8 * nw * step < r_end && active)     // keep HBM busy well ahead of the few resident warps
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ld * (next + 8 * nw * step + rsub)));
-        uint32_t b[R], c[R];
-        bool ok[R];
+        if (__builtin_expect(!plain, 0)) {      // a value at a bin edge, outside the limits or NaN: the exact rule for all R
 #pragma unroll
-        for (int k = 0; k < R; k++) {
-            ok[k] = active && row + (uint64_t)k * rpw + rsub < r_end;
-            b[k] = ok[k] ? hist_bin(v[k], lo, range, fbins, bins, scale, guard) : bins + k;   // sentinels never match
+            for (int k = 0; k < R; k++) b[k] = hist_bin_fx_call(x[k], lo, range, fbins, bins, scale_fx) * 32u;
         }
 #pragma unroll
-        for (int k = 0; k < R; k++) c[k] = mine[(ok[k] ? b[k] : 0u) * 32u];
+        for (int k = 0; k < R; k++) c[k] = mine[b[k]];
 #pragma unroll
         for (int k = 0; k < R; k++) {
             uint32_t same = 1;
@@ -474,10 +494,50 @@ __global__ void __launch_bounds__(512) k_hist_aos_lanes(const float* __restrict_
             c[k] += same;
         }
 #pragma unroll
-        for (int k = 0; k < R; k++)
-            if (ok[k]) mine[b[k] * 32u] = c[k];
+        for (int k = 0; k < R; k++) mine[b[k]] = (uint16_t)c[k];
+    };
+    if (active && s_begin < s_end) {
+        float v[RL], vn[RL];
+        uint32_t off = hop * s_begin + ldb * rsub + 4u * dl;           // this lane's element of its first row
+        const uint32_t off_last = hop * (s_end - 1) + ldb * rsub + 4u * dl;
+        uint32_t pk[RL];                                                // the lane's RL rows inside a step
 #pragma unroll
-        for (int k = 0; k < R; k++) v[k] = vn[k];
+        for (int k = 0; k < RL; k++) pk[k] = pitch * k;
+#pragma unroll
+        for (int k = 0; k < RL; k++) v[k] = __ldcs(reinterpret_cast<const float*>(cta + (off + pk[k])));
+        // The loads of one step ahead keep only a few KB in flight per SM, so the warp pulls its stream into L2 well
+        // ahead: every PFB steps, one lane per row, the first and the last line of the segments of the next block.
+        constexpr uint32_t PFB = 4;                                     // steps per prefetch block
+        const uint32_t pf_rows = PFB * step;                            // rows per block
+        const uint32_t pf_ahead = max(2u, 16u / rpw / PFB) * PFB;       // steps of lead
+        uint32_t until_pf = 0;
+        for (uint32_t s = s_begin; s < s_end; s++) {
+            off = min(off + hop, off_last);                             // the last step re-reads itself (unused)
+#pragma unroll
+            for (int k = 0; k < RL; k++) vn[k] = __ldcs(reinterpret_cast<const float*>(cta + (off + pk[k])));
+            if (until_pf == 0) {
+                until_pf = PFB;
+                if (s + pf_ahead + PFB <= s_end) {
+                    const char* blk = cta + (uint64_t)hop * (s + pf_ahead);
+                    for (uint32_t i = lane; i < pf_rows; i += 32) {
+                        const char* q = blk + i * ldb;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 4u * (width - 1)));
+                    }
+                }
+            }
+            until_pf--;
+#pragma unroll
+            for (int g = 0; g < G; g++) count_rows(v + g * R);
+#pragma unroll
+            for (int k = 0; k < RL; k++) v[k] = vn[k];
+        }
+    }
+    if (active && warp == nw - 1) {                                     // the ragged rest: fewer than `step` rows
+        for (uint32_t r = full * step + rsub; r < rows; r += rpw) {
+            const float x = __ldcs(reinterpret_cast<const float*>(cta + ((uint64_t)r * ldb + 4u * dl)));
+            mine[hist_bin_fx(x, lo, range, fbins, bins, scale_fx) * 32u] += 1;
+        }
     }
     __syncthreads();
     // fold the warps (and, in a narrow chunk, the lanes that served the same dimension); one global atomic per non-empty bin
@@ -486,7 +546,7 @@ __global__ void __launch_bounds__(512) k_hist_aos_lanes(const float* __restrict_
         if (x >= width) continue;
         uint32_t total = 0;
         for (uint32_t w = 0; w < nw; w++)
-            for (uint32_t q = 0; q < rpw; q++) total += sh[(w * bins + bin) * 32u + q * tp + x];
+            for (uint32_t q = 0; q < rpw; q++) total += sh16[(w * bins + bin) * 32u + q * tp + x];
         if (total) atomicAdd(&counts[(size_t)bins * (d0 + x) + bin], total);
     }
 }

@@ -68,7 +68,8 @@ __global__ void k_exp_inplace(uint32_t n, float* __restrict__ v) {
     if (i < n) v[i] = __expf(v[i]);
 }
 
-// evidence_reduce + sum_reduction (likelihood.cu:24-36): sum_i exp(loglik_i) accumulated in double
+// evidence_reduce + sum_reduction (likelihood.cu:24-36): sum_i exp(loglik_i) accumulated in double.  One partial per
+// CTA (acc[blockIdx.x]), added up by the host in CTA order: the same bits on every run, no floating-point atomics.
 __global__ void k_exp_sum(uint32_t n, const float* __restrict__ v, double* __restrict__ acc) {
     double s = 0.0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += (double)__expf(v[i]);
@@ -81,7 +82,7 @@ __global__ void k_exp_sum(uint32_t n, const float* __restrict__ v, double* __res
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (uint32_t w = 0; w < nw; w++) t += sm[w];
-        atomicAdd(acc, t);
+        acc[blockIdx.x] = t;
     }
 }
 

@@ -325,6 +325,31 @@ def test_dataset_engine_ragged_shapes(factory, n, m):
         assert np.array_equal(counts, orc.histogram_counts(data, m, n, G.WGS, lim).reshape(m, G.WGS))
 
 
+@pytest.mark.parametrize("wgs", [64, 256])
+@pytest.mark.parametrize("n,m", [(40_003, 100), (9_000, 64), (70_001, 3), (5_000, 36)])
+def test_dataset_histogram_repeated_bins(n, m, wgs):
+    """The lane-private histogram kernel adds, per lane, the number of its in-flight rows that share a bin: data with
+    few distinct values (whole runs of rows in one bin), a constant column and a +-inf / NaN sprinkle must still give
+    the oracle's integer counts."""
+    rng = np.random.default_rng(n + m + wgs)
+    data = rng.integers(0, 7, size=(n, m)).astype(np.float32)          # 7 distinct values per column
+    data[:, 1] = 2.5                                                     # zero range
+    data[::3, 2] = rng.standard_normal(len(data[::3, 2])).astype(np.float32)
+    if m > 40:
+        data[:, 40] = np.repeat(rng.standard_normal(n // 8 + 1), 8)[:n].astype(np.float32)   # runs of 8 equal rows
+        data[5, 33], data[6, 34], data[7, 35] = np.inf, -np.inf, np.nan
+    f = bb.B200BayaderaFactory(device=0, wgs=wgs)
+    try:
+        h, counts = f.dataset_engine().histogram(data, with_counts=True)
+        lim = orc.min_max(data, m, n)
+        assert np.array_equal(h.limits.reshape(-1), lim, equal_nan=True)
+        want = orc.histogram_counts(data, m, n, wgs, lim).reshape(m, wgs)
+        assert np.array_equal(counts, want)
+        assert int(counts.sum()) == n * m
+    finally:
+        f.release()
+
+
 # ------------------------------------------------------------------------- statistical end-to-end --
 def test_beta_binomial_posterior_matches_analytic(factory):
     """configs[1]: Beta(3,2) prior, N=50, z=15 -> Beta(18,37) (nvidia_gtx_test.clj:135-151) via mix!."""
