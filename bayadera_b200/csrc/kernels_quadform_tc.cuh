@@ -66,7 +66,8 @@ __host__ __device__ constexpr uint32_t np_of(uint32_t D) { return (D + 15u) / 16
 
 __host__ __device__ constexpr size_t smem_bytes() {
     // A: 2 planes x 2 chunks x 16 KB; B: 2 planes x 2 chunks x (128 rows x 128 B); per-walker arrays; slack
-    return 1024 + 4 * (size_t)A_CHUNK_BYTES + 4 * (size_t)A_CHUNK_BYTES + 8192;
+    // + the own rows of the next tile, one bulk copy per warp (128 rows x up to 512 B)
+    return 1024 + 4 * (size_t)A_CHUNK_BYTES + 4 * (size_t)A_CHUNK_BYTES + 8192 + (size_t)TILE * MAX_D * 4;
 }
 
 // byte offset of element (row r, k' < 64) inside a K-major SWIZZLE_128B operand tile (8-row atoms of 1024 B)
@@ -132,6 +133,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_quadform_move_tc(const __grid_co
     const uint32_t uscale = part + 4 * TILE * 4;              // [128] f32: 1 / scale of U's row i
     const uint32_t mbar = uscale + TILE * 4;                  // [2] u64: MMA(stage) complete
     const uint32_t tmem_slot = mbar + 16;
+    const uint32_t ybar = mbar + 32;                          // [16] u64: the own rows of warp w's 8 walkers have landed
+    const uint32_t ybuf = part + 8192;                        // [128 rows][DA] f32, row r at ybuf + r * 4 * DA
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const uint32_t nwalk = a.k_end - a.k_begin;
@@ -144,6 +147,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_quadform_move_tc(const __grid_co
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(1) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar + 8), "r"(1) : "memory");
+        for (uint32_t w = 0; w < THREADS / 32; w++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ybar + 8u * w), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -232,28 +237,39 @@ __global__ void __launch_bounds__(THREADS, 1) k_quadform_move_tc(const __grid_co
             lp_nxt = __ldcg(a.lp_active + kc);
             pj_nxt = reinterpret_cast<const float*>(a.xa_compl[j / a.hs]) + (size_t)j * DA;
         }
+        // the own rows of this warp — ONE contiguous block — travel into shared memory by a bulk copy (no registers in
+        // flight, read back in the convert phase); rows past the end of the slice are left out
+        if (lane == 0 && k0 < a.k_end) {
+            const uint32_t bytes = min((uint32_t)ROWS_PER_WARP, a.k_end - k0) * 4u * DA;
+            const uint32_t bar = ybar + 8u * warp;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(ybuf + row0 * 4u * DA), "l"(a.xa_active + (size_t)k0 * DA), "r"(bytes), "r"(bar) : "memory");
+        }
 #pragma unroll
         for (int i = 0; i < ROWS_PER_WARP; i++) {
             const unsigned long long p = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)pj_nxt, i);
-            const uint32_t k = min(k0 + (uint32_t)i, a.k_end - 1);
             Xj[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lane_on) {
-                // the random (possibly remote) partner row travels into registers now; the own rows — one contiguous
-                // block per tile — are only pulled into L2 and read in the convert phase (32 registers less in flight)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const float4*>(a.xa_active + (size_t)k * DA) + lane));
-                Xj[i] = __ldcg(reinterpret_cast<const float4*>(p) + lane);   // maybe another GPU's memory: never via L1
-            }
+            // the random (possibly remote) partner row travels into registers now
+            if (lane_on) Xj[i] = __ldcg(reinterpret_cast<const float4*>(p) + lane);   // maybe another GPU's memory: never via L1
         }
     };
 
     // proposal, centring, row scale, fp16 split -> operand tiles; keeps Y for the write-back
     auto convert_phase = [&](uint32_t it) {
         const uint32_t k0 = tile_k0(it) + row0;
+        if (k0 < a.k_end) {                                 // this warp's it-th bulk copy (warps past the end issue none)
+            const uint32_t bar = ybar + 8u * warp, parity = it & 1u;
+            uint32_t done;
+            do {
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            } while (!done);
+        }
 #pragma unroll
-        for (int i = 0; i < ROWS_PER_WARP; i++) {          // own rows (L2 hits): all loads in flight before the first use
-            const uint32_t k = min(k0 + (uint32_t)i, a.k_end - 1);
+        for (int i = 0; i < ROWS_PER_WARP; i++) {          // own rows out of shared memory
             Y[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lane_on) Y[i] = __ldcg(reinterpret_cast<const float4*>(a.xa_active + (size_t)k * DA) + lane);
+            if (lane_on) Y[i] = ldsf4(ybuf + (row0 + (uint32_t)i) * 4u * DA + 16u * lane);
         }
         float inv_mine = 1.0f;
 #pragma unroll
