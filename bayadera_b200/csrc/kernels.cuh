@@ -415,16 +415,17 @@ struct HistPlan {
 };
 
 // hist_bin in fixed point, for bins <= 256: q = round(t' * 4096) comes out of ONE FFMA against the rounding constant
-// 1.5 * 2^23 (no F2I / FRND, which run on the quarter-rate XU pipe).  The fast path is taken when t' is inside
-// [0.5, bins - 0.5) and q is not a multiple of 4096, i.e. t' is at least 1 / 8192 = 1.2e-4 away from an integer —
-// the approximate t' is within 1.8e-7 relative (4.6e-5 at the top bin) of the defining value, so floor(t') is the
-// bin; everything else (1 value in 4096, NaN, out of range) takes the exact path.
+// 1.5 * 2^23 (no F2I / FRND, which run on the quarter-rate XU pipe).  The fast path is taken when 0 < q < bins * 4096
+// and q is not a multiple of 4096, i.e. t' is inside (0, bins) and at least 1 / 8192 = 1.2e-4 away from every
+// integer — the approximate t' is within 1.8e-7 relative (4.6e-5 at the top bin) of the defining value, so
+// floor(t') is the bin; everything else (1 value in 4096, NaN, out of range) takes the exact path
+// (tests/test_hist_fixed_point.py restates this arithmetic in numpy and checks the claim).
 constexpr float HIST_FX = 4096.f;
-__device__ __forceinline__ bool hist_fx_plain(uint32_t q, uint32_t span) { return (q - 2048u) < span && (q & 4095u) != 0u; }
+__device__ __forceinline__ bool hist_fx_plain(uint32_t q, uint32_t span) { return q < span && (q & 4095u) != 0u; }
 __device__ __forceinline__ uint32_t hist_bin_fx(float x, float lo, float range, float fbins, uint32_t bins, float scale_fx) {
     const float d = __fsub_rn(x, lo);
     const uint32_t q = __float_as_uint(fmaf(d, scale_fx, 12582912.f)) - 0x4B400000u;
-    if (__builtin_expect(hist_fx_plain(q, bins * 4096u - 4096u), 1)) return q >> 12;
+    if (__builtin_expect(hist_fx_plain(q, bins * 4096u), 1)) return q >> 12;
     return hist_bin_exact(d, range, fbins, bins);
 }
 
@@ -456,7 +457,7 @@ __global__ void __launch_bounds__(512) k_hist_aos_lanes(const float* __restrict_
     const uint32_t d = d0 + (active ? dl : 0u);
     const float lo = limits[2 * d], range = __fsub_rn(limits[2 * d + 1], lo);
     const float fbins = (float)bins, scale_fx = __fdividef(fbins * HIST_FX, range);
-    const uint32_t span = bins * 4096u - 4096u;
+    const uint32_t span = bins * 4096u;
     __syncthreads();
     uint16_t* mine = sh16 + warp * bins * 32u + lane;
     // rows of this CTA: [r_begin, r_begin + rows), rows <= 65535 and rows * ld * 4 < 2^32 (the host sees to both).
