@@ -524,8 +524,8 @@ def main():
                 "note": "achieved counts ALGORITHMIC flops (2*rows*D per walker).  fp32-level accuracy on 16-bit tensor-core "
                         f"inputs takes {terms} MMAs per product (theta - theta0 and the dataset in two fp16 pieces each; three "
                         "bf16 pieces of theta with BAY_GLM_TERMS=4), so the tensor pipe executes that multiple of the "
-                        f"algorithmic flops and frac cannot exceed 1/{terms}; the kernel's binding unit is the XU (exp2) pipe, "
-                        "see DESIGN.md 4.2 for the pipe utilisations ncu reports",
+                        f"algorithmic flops and frac cannot exceed 1/{terms}; the kernel runs at the board's power cap (see clocks.reasons) "
+                        "with the XU (exp2) pipe 87 % busy; DESIGN.md 4.2 has the pipe utilisations ncu reports",
                 "hbm_view": {"bytes_per_launch": flops_per_launch / min(W // 2, per) * 2.0,
                              "achieved_GBps": flops_per_launch / min(W // 2, per) * 2.0 / (per_launch_ms * 1e-3) / 1e9,
                              "note": "dataset bytes (bf16 hi+lo planes = 4 B/element) streamed from HBM once per launch"}}
