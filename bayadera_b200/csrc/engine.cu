@@ -1252,9 +1252,13 @@ static int quadform_half(bay_sampler* s, int half, uint32_t seed, uint32_t tag, 
                          float beta, uint32_t step) {
     bay_model* m = s->m;
     bay_engine* e = m->e;
-    const size_t smem = bay::qf::smem_bytes();
+    const bool bulk = !partitioned(s);
+    const size_t smem = bay::qf::smem_bytes(bulk);
     if (!s->qf_configured) {
-        CK(cudaFuncSetAttribute(bay::qf::k_quadform_move_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(bay::qf::k_quadform_move_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)bay::qf::smem_bytes(true)));
+        CK(cudaFuncSetAttribute(bay::qf::k_quadform_move_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)bay::qf::smem_bytes(false)));
         s->qf_configured = true;
     }
     bay::qf::Args a;
@@ -1283,7 +1287,8 @@ static int quadform_half(bay_sampler* s, int half, uint32_t seed, uint32_t tag, 
     a.accepted = nullptr;
     const uint32_t tiles = cdiv(a.k_end - a.k_begin, bay::qf::TILE);
     uint32_t grid = (uint32_t)e->sm_count < tiles ? (uint32_t)e->sm_count : tiles;
-    bay::qf::k_quadform_move_tc<<<grid, bay::qf::THREADS, smem, e->stream>>>(a);
+    if (!bulk) bay::qf::k_quadform_move_tc<false><<<grid, bay::qf::THREADS, smem, e->stream>>>(a);
+    else bay::qf::k_quadform_move_tc<true><<<grid, bay::qf::THREADS, smem, e->stream>>>(a);
     CKLAUNCH();
     s->soa_own_stale = true;
     return exchange_half(s, half);

@@ -64,10 +64,12 @@ struct Args {
 
 __host__ __device__ constexpr uint32_t np_of(uint32_t D) { return (D + 15u) / 16u * 16u; }   // padded N = padded K
 
-__host__ __device__ constexpr size_t smem_bytes() {
+__host__ __device__ constexpr size_t smem_bytes(bool bulk) {
     // A: 2 planes x 2 chunks x 16 KB; B: 2 planes x 2 chunks x (128 rows x 128 B); per-walker arrays; slack
-    // + the own rows of the next tile, one bulk copy per warp (128 rows x up to 512 B)
-    return 1024 + 4 * (size_t)A_CHUNK_BYTES + 4 * (size_t)A_CHUNK_BYTES + 8192 + (size_t)TILE * MAX_D * 4;
+    // bulk: + the own rows of the next tile, one bulk copy per warp (128 rows x up to 512 B).  The walker-partitioned
+    // instantiation does without: every KB of shared memory is taken from L1, and in-flight REMOTE loads are staged
+    // there — with 205 KB of shared memory the same kernel pulled 16 % slower over NVLink (152 vs 128 us at 2 GPUs).
+    return 1024 + 4 * (size_t)A_CHUNK_BYTES + 4 * (size_t)A_CHUNK_BYTES + 8192 + (bulk ? (size_t)TILE * MAX_D * 4 : 0);
 }
 
 // byte offset of element (row r, k' < 64) inside a K-major SWIZZLE_128B operand tile (8-row atoms of 1024 B)
@@ -117,6 +119,10 @@ __device__ __forceinline__ float4 ldsf4(uint32_t addr) {
     return v;
 }
 
+// BULK: the own rows of a tile travel by one cp.async.bulk per warp into shared memory (+2 % on one GPU).  The walker-
+// partitioned sampler instantiates BULK = false — own rows prefetched into L2, read by ld.global.cg when converted —
+// because the extra 64 KB of shared memory cost it NVLink throughput (see smem_bytes).
+template <bool BULK>
 __global__ void __launch_bounds__(THREADS, 1) k_quadform_move_tc(const __grid_constant__ Args a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     // everything below is addressed by 32-bit SHARED addresses (no generic pointers: those cost a descriptor move per
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_quadform_move_tc(const __grid_co
         }
         // the own rows of this warp — ONE contiguous block — travel into shared memory by a bulk copy (no registers in
         // flight, read back in the convert phase); rows past the end of the slice are left out
-        if (lane == 0 && k0 < a.k_end) {
+        if (BULK && lane == 0 && k0 < a.k_end) {
             const uint32_t bytes = min((uint32_t)ROWS_PER_WARP, a.k_end - k0) * 4u * DA;
             const uint32_t bar = ybar + 8u * warp;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -250,15 +256,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_quadform_move_tc(const __grid_co
         for (int i = 0; i < ROWS_PER_WARP; i++) {
             const unsigned long long p = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)pj_nxt, i);
             Xj[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            // the random (possibly remote) partner row travels into registers now
-            if (lane_on) Xj[i] = __ldcg(reinterpret_cast<const float4*>(p) + lane);   // maybe another GPU's memory: never via L1
+            if (lane_on) {
+                if (!BULK) {   // own rows: only pulled into L2 here
+                    const uint32_t k = min(k0 + (uint32_t)i, a.k_end - 1);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const float4*>(a.xa_active + (size_t)k * DA) + lane));
+                }
+                // the random (possibly remote) partner row travels into registers now
+                Xj[i] = __ldcg(reinterpret_cast<const float4*>(p) + lane);   // maybe another GPU's memory: never via L1
+            }
         }
     };
 
     // proposal, centring, row scale, fp16 split -> operand tiles; keeps Y for the write-back
     auto convert_phase = [&](uint32_t it) {
         const uint32_t k0 = tile_k0(it) + row0;
-        if (k0 < a.k_end) {                                 // this warp's it-th bulk copy (warps past the end issue none)
+        if (BULK && k0 < a.k_end) {                         // this warp's it-th bulk copy (warps past the end issue none)
             const uint32_t bar = ybar + 8u * warp, parity = it & 1u;
             uint32_t done;
             do {
@@ -269,7 +281,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_quadform_move_tc(const __grid_co
 #pragma unroll
         for (int i = 0; i < ROWS_PER_WARP; i++) {          // own rows out of shared memory
             Y[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lane_on) Y[i] = ldsf4(ybuf + (row0 + (uint32_t)i) * 4u * DA + 16u * lane);
+            if (lane_on) {
+                if (BULK) Y[i] = ldsf4(ybuf + (row0 + (uint32_t)i) * 4u * DA + 16u * lane);
+                else Y[i] = __ldcg(reinterpret_cast<const float4*>(a.xa_active + (size_t)min(k0 + (uint32_t)i, a.k_end - 1) * DA) + lane);
+            }
         }
         float inv_mine = 1.0f;
 #pragma unroll
