@@ -1,5 +1,6 @@
 #!/bin/bash
 # A/B of the walker-partitioned quadratic-form move on the SAME box: in-tree library vs bayadera_b200/variants/libbay_oldqf.so
+# (build the other variant first: nvcc ... -shared -o bayadera_b200/variants/libbay_oldqf.so <other tree>/bayadera_b200/csrc/engine.cu)
 N=${1:-2}
 mkdir -p gpurun_out
 for v in new old new old; do
