@@ -350,6 +350,22 @@ def test_dataset_histogram_repeated_bins(n, m, wgs):
         f.release()
 
 
+def test_dataset_histogram_more_than_256_bins_uses_the_atomic_kernel():
+    """WGS = 512 bins: the lane-private kernel covers up to 256, so this is k_hist_aos (shared-memory atomics)."""
+    n, m, wgs = 30_011, 40, 512
+    rng = np.random.default_rng(5)
+    data = (rng.standard_normal((n, m)) * 2 + 1).astype(np.float32)
+    data[:, 3] = rng.integers(0, 5, n).astype(np.float32)
+    f = bb.B200BayaderaFactory(device=0, wgs=wgs)
+    try:
+        h, counts = f.dataset_engine().histogram(data, with_counts=True)
+        lim = orc.min_max(data, m, n)
+        assert np.array_equal(h.limits.reshape(-1), lim)
+        assert np.array_equal(counts, orc.histogram_counts(data, m, n, wgs, lim).reshape(m, wgs))
+    finally:
+        f.release()
+
+
 # ------------------------------------------------------------------------- statistical end-to-end --
 def test_beta_binomial_posterior_matches_analytic(factory):
     """configs[1]: Beta(3,2) prior, N=50, z=15 -> Beta(18,37) (nvidia_gtx_test.clj:135-151) via mix!."""
